@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the PyCGTOOL hot path on B200 (driver contract: one JSON line on stdout).
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   the reference algorithm on the host CPUs
+
+Workload (BASELINE.json configs[1], "S2"): map-only DOPC/POPC membrane, 1,152 lipids,
+N = 156,672 atoms -> B = 13,824 MARTINI beads, 10,000 frames, synthetic coordinates
+(molecules straddle the periodic box).  A *step* is one pass of the mapping over the whole
+10,000-frame trajectory.  Metric: atom-frames/s.
+
+* ``value``      device-resident throughput: inputs already in HBM, CUDA events around K steps.
+* ``e2e``        the same metric through the public API (``Mapping.apply``) with HOST buffers:
+                 pinned host -> device copies, the kernel and the device -> host copy of the bead
+                 coordinates are all inside the timed region (on a bounded frame batch, stated).
+* ``roofline``   HBM roofline of the dominant kernel (K1 ``map_tiles_kernel``): algorithmic bytes
+                 F*(12N + 12B + 12) per launch / CUDA-event duration, against MEASURED_PEAKS.json.
+* ``cpu_baseline`` the oracle (NumPy restatement of the reference, its loop structure kept) timed on
+                 the host cores on a bounded frame sample.
+* ``measure``    supplementary: bonded-term measurement (K2) on config S3 (1 M frames, 66 terms).
+
+Multi-GPU (torchrun, one rank per GPU): frames are independent, so every rank maps its own
+10,000-frame shard with no data-path collective (weak scaling); value = all atom-frames / max time.
+"""
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+S2_FRAMES = 10000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="s2", choices=["s2", "s4", "s5"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (0 = the config's own)")
+    ap.add_argument("--e2e-frames", type=int, default=2048)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / e2e / measure legs")
+    ap.add_argument("--ref-frames-per-worker", type=int, default=128)
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        data = json.loads(path.read_text())
+        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = f"/tmp/cgb_clocks_{os.getpid()}.csv"
+
+    def __enter__(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.out.close()
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                      parts[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------
+def make_system(name):
+    from pycgtool_b200 import synth
+    if name == "s2":
+        return synth.s2(), S2_FRAMES, "S2 map-only DOPC/POPC membrane: 1,152 lipids, N=156,672 atoms -> 13,824 beads, 10,000 frames"
+    if name == "s4":
+        return synth.s4(), 2000, "S4 5M-atom solvated membrane: N=4,999,872 atoms -> 417,424 beads, 2,000 frames"
+    return synth.s5(), 512, "S5 20M-atom multi-lipid membrane: N=19,999,992 atoms -> 1,710,442 beads, 512 frames"
+
+
+def oracle_residue_lists(topology):
+    top = topology
+    return [(top.res_names[top.res_name_id[r]],
+             [top.atom_names[i] for i in top.atom_name_id[top.res_first[r]:top.res_first[r + 1]]])
+            for r in range(top.n_residues)]
+
+
+def _oracle_map_chunk(args):
+    """Worker of the reference arm: the oracle's Mapping.apply on one frame block."""
+    map_path, residues, seed_sys, first, count = args
+    from oracle import mapping as omap, system as osystem
+    xyz = seed_sys.coordinates_host(count, first_frame=first)
+    box = seed_sys.box_vectors(count, first_frame=first)
+    sysm = osystem.from_residue_lists(residues, xyz, box)
+    mols = omap.parse_map(map_path)
+    t0 = time.perf_counter()
+    cg = omap.apply(mols, sysm)
+    dt = time.perf_counter() - t0
+    return dt, float(cg.xyz[0, 0, 0])
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port -- mdtraj cannot be installed, so
+    the reference itself cannot be imported) on the host cores, all of them, bounded frame sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    sysm, frames, label = make_system(args.workload)
+    map_path, _ = sysm.write_files()
+    residues = oracle_residue_lists(sysm.topology)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    per_worker = args.ref_frames_per_worker
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            jobs = [(str(map_path), residues, sysm, (step * cores + w) * per_worker % max(frames - per_worker, 1),
+                     per_worker) for w in range(cores)]
+            t0 = time.perf_counter()
+            # coordinates are generated inside the workers before their timer starts; the wall time of
+            # the step is the slowest worker's mapping time (workers run concurrently)
+            results = pool.map(_oracle_map_chunk, jobs)
+            wall = time.perf_counter() - t0
+            slowest = max(r[0] for r in results)
+            if step >= args.warmup:
+                times.append(slowest)
+            del wall
+    units = cores * per_worker * sysm.n_atoms
+    total = sum(times)
+    value = units * len(times) / total
+    sample = f"{cores * per_worker} frames per step ({per_worker} per worker x {cores} workers) of the {frames}-frame config"
+    line = {
+        "metric": "atom-frames/s", "value": value, "unit": "atom-frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": label, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "atom-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "atom-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(sysm, map_path, frames_total, sample_frames=512):
+    """Single-threaded oracle (the reference is single-threaded) on a bounded frame sample."""
+    from oracle import mapping as omap, system as osystem
+    residues = oracle_residue_lists(sysm.topology)
+    xyz = sysm.coordinates_host(sample_frames)
+    box = sysm.box_vectors(sample_frames)
+    osys = osystem.from_residue_lists(residues, xyz, box)
+    mols = omap.parse_map(map_path)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        omap.apply(mols, osys)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": sample_frames * sysm.n_atoms / best, "unit": "atom-frames/s", "cores": 1, "kind": "port",
+            "sample": f"{sample_frames} of {frames_total} frames, single thread (the reference is single-threaded), "
+                      f"best of 2, host has {os.cpu_count()} cores"}
+
+
+def measure_leg(dev, peak_gbs):
+    """Supplementary: K2 (bond measurement + statistics) on config S3, device resident."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200.synth import Options
+    sysm = synth.small_molecule()
+    n_frames = 1 << 20
+    map_path, bnd_path = sysm.write_files()
+    xyz = sysm.coordinates_device(n_frames, dev, chunk=1 << 16)
+    box = sysm.box_vectors(n_frames)
+    mapper = Mapping(map_path, Options())
+    cg = mapper.apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz))
+    del xyz
+    bonds = BondSet(bnd_path, Options())
+    for _ in range(2):
+        bonds.apply(cg)
+    torch.cuda.synchronize()
+    reps = 5
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        bonds.apply(cg)
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    t0 = time.perf_counter()
+    bonds.boltzmann_invert()
+    torch.cuda.synchronize()
+    invert_ms = 1e3 * (time.perf_counter() - t0)
+    n_terms = 66
+    measures = n_frames * n_terms
+    bytes_alg = n_frames * (12 * 24 + 4 * n_terms + 36)
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    return {"workload": "S3 small molecule: 24 beads, 66 terms (23 bonds, 22 angles, 21 dihedrals), 1,048,576 frames",
+            "value": measures / (ms * 1e-3), "unit": "bond-measures/s", "ms_per_pass": ms,
+            "includes": "shift pre-pass + values + moments + circular sums + 128-bin histograms (3 launches + 3 tiny)",
+            "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak_gbs,
+            "boltzmann_invert_ms": invert_ms}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as td
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+
+    from pycgtool_b200 import Frame, Mapping, _lib
+    from pycgtool_b200.synth import Options
+    lib = _lib.load()            # fails loudly if the CUDA library is missing
+
+    peak_gbs, peak_src = load_peaks()
+    sysm, frames, label = make_system(args.workload)
+    if args.frames:
+        frames = args.frames
+    map_path, _ = sysm.write_files()
+    mapper = Mapping(map_path, Options())
+    plan = mapper.compile_plan(sysm.topology)
+    n_atoms, n_beads = sysm.n_atoms, plan.n_beads
+
+    # each rank owns its own frame shard (different frames: first_frame offset), resident in HBM
+    xyz = sysm.coordinates_device(frames, dev, first_frame=rank * frames)
+    box_np = sysm.box_vectors(frames, first_frame=rank * frames)
+    lengths = torch.from_numpy(np.stack([box_np[:, 0, 0], box_np[:, 1, 1], box_np[:, 2, 2]], axis=1)).to(dev)
+    out = torch.empty((frames, n_beads, 3), dtype=torch.float32, device=dev)
+    d = Mapping._device_plan(plan, dev)
+
+    def step():
+        mapper.map_device(plan, xyz, lengths, out=out)
+
+    launches_per_step = (1 if d["n_tiles"] else 0) + (1 if d["n_wide"] else 0) + (1 if d["n_virt"] else 0)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            step()
+        stop.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize()
+    elapsed_ms = start.elapsed_time(stop)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    units_per_step = world * frames * n_atoms
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel on this rank (one K1 launch per step)
+    bytes_per_launch = frames * (12 * n_atoms + 12 * n_beads + 12)
+    own_ms = start.elapsed_time(stop) / args.steps
+    achieved = bytes_per_launch / (own_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "kernel": "cgb::map_tiles_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    traffic_file = ROOT / "profiles" / "k1_traffic.json"
+    if traffic_file.exists():
+        try:
+            tr = json.loads(traffic_file.read_text())
+            if tr.get("workload") == args.workload and tr.get("frames") == frames:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+        except (ValueError, KeyError):
+            pass
+
+    # ---------------- e2e: public API with host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_extras:
+        ef = min(frames, args.e2e_frames)
+        host = torch.empty((ef, n_atoms, 3), dtype=torch.float32, pin_memory=True)
+        host.copy_(xyz[:ef])
+        torch.cuda.synchronize()
+        import pycgtool_b200.mapping as pm
+        pm.STREAM_THRESHOLD_BYTES = 0
+        frame = Frame.from_arrays(sysm.topology, host.numpy(), unitcell_vectors=box_np[:ef])
+        for _ in range(2):
+            cg = mapper.apply(frame)
+            _ = cg._trajectory.xyz
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        reps = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cg = mapper.apply(frame)
+            res = cg._trajectory.xyz            # host copy of the bead coordinates
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": world * ef * n_atoms / dt, "unit": "atom-frames/s",
+               "h2d_bytes_per_step": ef * n_atoms * 12 + ef * 12, "d2h_bytes_per_step": int(res.nbytes),
+               "frames_per_step": ef, "ms_per_step": dt * 1e3,
+               "note": "Mapping.apply on a pinned host trajectory: chunked H2D -> K1 -> D2H pipeline; PCIe-bound"}
+        del host, frame, cg
+
+    clock_info = clocks.summary()
+    line = {
+        "metric": "atom-frames/s", "value": value, "unit": "atom-frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "b200",
+        "config": {"workload": label, "frames_per_gpu": frames, "n_atoms": n_atoms, "n_beads": n_beads,
+                   "l2": "inputs larger than L2 (18.8 GB per pass), no flush needed",
+                   "parallelism": f"frame-sharded x{world}, no data-path collective"},
+        "roofline": roofline, "clocks": clock_info, "gpu_launches": launches_per_step * args.steps,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_extras:
+        del xyz, out
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_leg(sysm, map_path, frames)
+        try:
+            line["measure"] = measure_leg(dev, peak_gbs)
+        except Exception as exc:  # supplementary leg must not take the headline down
+            line["measure"] = {"error": repr(exc)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+/*
+ * pycgtool_b200.h -- C ABI of libpycgtool_b200.so
+ *
+ * B200 (sm_100a) implementation of PyCGTOOL's per-frame hot path:
+ *   stage 1  atom -> bead mapping            (reference pycgtool/mapping.py:391-463)
+ *   stage 2  bonded-term measurement + stats (reference pycgtool/bondset.py:496-531, which calls
+ *            mdtraj.compute_distances/angles/dihedrals, and pycgtool/util.py:24-53)
+ *   stage 3  Boltzmann inversion             (reference pycgtool/bondset.py:62-91,533-539 and
+ *            pycgtool/functionalforms.py:92-148)
+ *
+ * The reference is pure Python and has no FFI of its own; these entry points are what a ctypes
+ * binding inside Mapping.apply / BondSet.apply / BondSet.boltzmann_invert would call (see
+ * INTEGRATION.md).  Conventions:
+ *   - plain pointers and sizes only; no C++ or torch types cross the boundary;
+ *   - "device" pointers are CUDA device memory owned by the caller; "host" pointers are ordinary memory;
+ *   - every launch is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream)
+ *     and returns without synchronising; the library keeps no global state and allocates nothing;
+ *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative CGB_E* on bad arguments;
+ *   - all index tables are int32; frames, atoms and beads are counted in int64.
+ */
+#ifndef PYCGTOOL_B200_H
+#define PYCGTOOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGB_ABI_VERSION 1
+
+enum {
+    CGB_OK = 0,
+    CGB_EINVAL = -1,      /* NULL pointer, negative size, inconsistent table */
+    CGB_ERANGE = -2,      /* index outside the atom / bead range */
+    CGB_ETOOBIG = -3,     /* a single bead spans more atoms than a shared-memory tile can hold */
+    CGB_EALIGN = -4       /* pointer not aligned to its element type */
+};
+
+/* Human-readable text for any return code of this library (CUDA codes included). */
+const char* cgb_strerror(int code);
+int cgb_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1: mapping.
+ *
+ * Bead b (output order = reference CG topology order, mapping.py:359-389) is defined by the CSR row
+ * index[bead_ptr[b] .. bead_ptr[b+1]) with one weight per entry.  For a real bead the entries are
+ * global atom indices inside one residue (mapping.py:419-429); the first entry is the reference atom.
+ *   n == 1 : bead = x[a0]
+ *   n  > 1 : v_i = x[a_i] - x[a0];  if box: v_i -= L * rint(v_i / L)   (L = unit-cell *lengths* of the
+ *            frame; IEEE divide, round-half-even, no fused multiply-add);
+ *            bead = (sum_i w_i * v_i, summed in entry order) + x[a0]      (mapping.py:446-463)
+ * Arithmetic is float32 when the weights are float32 and float64 when they are float64 (ITP mass
+ * weights, mapping.py:224-227), the result is stored as float32 either way (frame.py:248).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One shared-memory tile of the mapping plan (32 bytes). */
+typedef struct CgbMapTile {
+    int32_t atom0;    /* first atom of the contiguous input span the tile stages   */
+    int32_t span;     /* atoms in that span                                         */
+    int32_t bead0;    /* first output bead of the tile                              */
+    int32_t nbeads;   /* output beads of the tile (contiguous in the output)        */
+    int64_t ent0;     /* offset of the tile's first entry in the entry array        */
+    int32_t nslots;   /* ELL depth: max atoms per bead in this tile                 */
+    int32_t reserved;
+} CgbMapTile;
+
+/* One ELL entry (8 bytes).  Entries of a tile are slot-major: entry(slot, j) = ent0 + slot*nbeads + j.
+ * slot 0: off3 = 3 * (reference atom - atom0), bits = atom count of the bead (0 = bead not computed by
+ * this kernel, e.g. a virtual bead).  slot >= 1: off3 = 3 * (atom - atom0), bits = float32 weight bits
+ * (padding entries repeat the reference atom with weight 0). */
+typedef struct CgbMapEntry {
+    int32_t off3;
+    int32_t bits;
+} CgbMapEntry;
+
+/* Host-side plan compiler, pass 1: count tiles / entries for a CSR mapping restricted to the beads
+ * with compute[b] != 0 (compute == NULL means all).  max_span_atoms bounds the input span of a tile
+ * and max_tile_beads its bead count.  All pointers are HOST pointers. */
+int cgb_map_plan_size(const int32_t* bead_ptr, const int32_t* index, const uint8_t* compute,
+                      int64_t n_beads, int64_t n_atoms, int32_t max_span_atoms, int32_t max_tile_beads,
+                      int64_t* n_tiles, int64_t* n_entries, int32_t* max_span, int32_t* max_tile_entries);
+
+/* Pass 2: fill caller-allocated HOST arrays sized by pass 1.  `weights` is float32[nnz] or
+ * float64[nnz] (weights_f64 != 0); entries_w64 (float64 per entry) is written only in the latter case
+ * and may be NULL otherwise. */
+int cgb_map_plan_build(const int32_t* bead_ptr, const int32_t* index, const void* weights, int weights_f64,
+                       const uint8_t* compute, int64_t n_beads, int64_t n_atoms,
+                       int32_t max_span_atoms, int32_t max_tile_beads,
+                       CgbMapTile* tiles, CgbMapEntry* entries, double* entries_w64);
+
+/* K1: tiled mapping kernel.  xyz: device float32 [F][N][3]; box_len: device float32 [F][3] or NULL
+ * (no periodic unwrap -- the caller passes NULL when the frame has no box or any length of any frame
+ * is zero, mapping.py:406-408); tiles/entries(/entries_w64): device copies of the plan; cg_xyz: device
+ * float32 [F][B][3].  Beads not covered by the plan are left untouched. */
+int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms, int64_t n_beads,
+                  const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries, const double* entries_w64,
+                  int32_t max_span, int32_t max_tile_entries, float* cg_xyz, void* stream);
+
+/* K1g: gather kernel over a CSR list, used for virtual beads (src = cg_xyz, mapping.py:431-438) and as
+ * the path for beads too wide for a tile.  bead_list: device int32[n_list] of output beads to compute. */
+int cgb_map_gather(const float* src, int64_t src_atoms, const float* box_len, int64_t n_frames, int64_t n_beads,
+                   const int32_t* bead_ptr, const int32_t* index, const void* weights, int weights_f64,
+                   const int32_t* bead_list, int64_t n_list, float* cg_xyz, void* stream);
+
+/* Tunables of K1 (0 keeps the built-in default): frames per pipeline stage byte budget, pipeline
+ * depth, frames per CTA.  Intended for benchmarking; not needed for correctness. */
+int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta);
+/* More K1 benchmarking knobs: consumer threads per CTA (multiple of 32, <= 256) and frames per register
+ * group (1, 2 or 4); 0 keeps the default. */
+int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2: bonded-term measurement with streaming statistics.
+ *
+ * A "column" is one instance of one bonded term (bondset.py:509-528); columns are ordered lengths,
+ * then angles, then dihedrals (n2, n3, n4 of them).  col_beads: device int32 [M][4] bead indices
+ * (unused trailing entries repeat the last bead); col_bond: device int32 [M] owning Bond.
+ * values: device float32 [F][M] (frame-major; Bond.values = values[:, cols of the bond].flatten()).
+ *   length   |mic(x1 - x0)|                                         (mdtraj compute_distances)
+ *   angle    acos(u.v / |u||v|), u = mic(x0 - x1), v = mic(x2 - x1)  (mdtraj compute_angles)
+ *   dihedral atan2((b1.c1)|b2|, c1.c2), b_i = mic(x_i - x_{i-1}), c1 = b2 x b3, c2 = b1 x b2
+ *                                                                   (mdtraj compute_dihedrals)
+ * box_vec: device float32 [F][9] rows a,b,c, or NULL (no unit cell).  ortho != 0 selects the
+ * orthorhombic minimum image (box diagonal), else the triclinic one (reduce, subtract, 27 images).
+ *
+ * partials: device float64 [n_bonds][CGB_NPART], ACCUMULATED into (caller zeroes it once; per-GPU
+ * shards are summed with an allreduce):
+ *   [0] count of finite values        [1] sum (v - shift)       [2] sum (v - shift)^2
+ *   [3] sum cos v                     [4] sum sin v             [5] sum wrap(v - circular mean)^2 (pass 2)
+ *   [6] count of all values           [7] reserved
+ * shift: device float32 [n_bonds] or NULL (0) -- any value near the data, identical on all shards.
+ * hist: device uint64 [n_bonds][n_bins] accumulated, or NULL; bin edges are
+ * linspace(hist_lo[b], hist_hi[b], n_bins + 1) with numpy.histogram's edge rules.
+ * ---------------------------------------------------------------------------------------------- */
+#define CGB_NPART 8
+
+int cgb_measure(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
+                const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
+                int64_t n_bonds, const float* shift, float* values, double* partials,
+                unsigned long long* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
+                void* stream);
+
+/* Pass 2 for dihedral columns: partials[b][5] += sum over the bond's values of wrap(v - m_b)^2 with
+ * m_b = atan2(partials[b][4], partials[b][3]) (util.py:40-53).  Call after partials[.][3..4] are final
+ * (i.e. after the cross-GPU reduction).  Columns [col_begin, col_begin + n_cols) of `values` are read. */
+int cgb_circular_pass2(const float* values, int64_t n_frames, int64_t n_cols_total,
+                       const int32_t* col_bond, int64_t col_begin, int64_t n_cols,
+                       double* partials, void* stream);
+
+/* Statistics of a caller-supplied value array for ONE Bond (Bond.boltzmann_invert on values that were
+ * not measured by cgb_measure, bondset.py:72-74): accumulates slots [0..4] and [6] of one partials row.
+ * values: device float32 [n]; natoms in {2,3,4} selects which sums are meaningful. */
+int cgb_value_stats(const float* values, int64_t n, int natoms, float shift, double* partials_row, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3: Boltzmann inversion (one thread per Bond).
+ *   natoms[b] in {2,3,4}; form[b] is a CGB_FORM_* id; RT = 8.314 * temperature / 1000.
+ *   out: device float64 [n_bonds][4] = { eqm, fconst, mean, variance }
+ *   lengths: arithmetic mean / population variance; angles and dihedrals: circular mean / variance;
+ *   dihedral eqm = ((mean) mod 2pi) - pi (bondset.py:81-84); variance == 0 -> fconst = +inf
+ *   (bondset.py:89-91); a bond with no finite values yields NaN in all four slots.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    CGB_FORM_HARMONIC = 0,            /* RT / var                       functionalforms.py:101-104 */
+    CGB_FORM_COSHARMONIC = 1,         /* RT / (sin^2(mean) * var)       functionalforms.py:117-121 */
+    CGB_FORM_MARTINI_LENGTH = 2,      /* 1250                           functionalforms.py:129-132 */
+    CGB_FORM_MARTINI_ANGLE = 3,       /* 25                             functionalforms.py:138-141 */
+    CGB_FORM_MARTINI_DIHEDRAL = 4,    /* 50                             functionalforms.py:147-148 */
+    CGB_FORM_STATS_ONLY = 5           /* user-defined form: only mean/variance are produced */
+};
+
+int cgb_boltzmann(const double* partials, const float* shift, const int32_t* natoms, const int32_t* form,
+                  double temperature, int64_t n_bonds, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCGTOOL_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of ``libpycgtool_b200.so`` (declared in ``include/pycgtool_b200.h``).
+
+There is no fallback: if the library is missing or a call fails, a
+``RuntimeError`` is raised.
+"""
+
+import ctypes
+import pathlib
+
+_CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
+LIBRARY_PATH = _CSRC / "libpycgtool_b200.so"
+
+NPART = 8  # CGB_NPART
+
+FORM_IDS = {
+    "Harmonic": 0,
+    "CosHarmonic": 1,
+    "MartiniDefaultLength": 2,
+    "MartiniDefaultAngle": 3,
+    "MartiniDefaultDihedral": 4,
+}
+FORM_STATS_ONLY = 5
+
+
+class MapTile(ctypes.Structure):
+    _fields_ = [
+        ("atom0", ctypes.c_int32),
+        ("span", ctypes.c_int32),
+        ("bead0", ctypes.c_int32),
+        ("nbeads", ctypes.c_int32),
+        ("ent0", ctypes.c_int64),
+        ("nslots", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/pycgtool_b200.h one to one
+SIGNATURES = {
+    "cgb_strerror": (ctypes.c_char_p, [_int]),
+    "cgb_abi_version": (_int, []),
+    "cgb_map_plan_size": (_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cgb_map_plan_build": (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "cgb_map_tiles": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
+    "cgb_map_set_tuning": (_int, [_i32, _i32, _i32]),
+    "cgb_map_set_shape": (_int, [_i32, _i32]),
+    "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
+                           _vp, _vp, _vp, _i32, _vp]),
+    "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "cgb_value_stats": (_int, [_vp, _i64, _int, ctypes.c_float, _vp, _vp]),
+    "cgb_boltzmann": (_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIBRARY_PATH.exists():
+        raise RuntimeError(
+            f"{LIBRARY_PATH} is missing: build it with `python -m pycgtool_b200.build` "
+            "(pycgtool_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(str(LIBRARY_PATH))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.cgb_abi_version() != 1:
+        raise RuntimeError("libpycgtool_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code, what="libpycgtool_b200 call"):
+    """Turn a non-zero return code into an exception."""
+    if code != 0:
+        text = load().cgb_strerror(code).decode()
+        raise RuntimeError(f"{what} failed with code {code}: {text}")
+
+
+def ptr(array):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if array is None:
+        return None
+    if not array.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return array.ctypes.data

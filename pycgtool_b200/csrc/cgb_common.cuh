@@ -1,0 +1,101 @@
+// Shared device/host helpers for libpycgtool_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pycgtool_b200.h"
+
+#define CGB_CUDA_TRY(expr)                         \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+namespace cgb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------- mbarrier + bulk-copy (TMA) PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+// Make barrier initialisation visible to the async (TMA) proxy.
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk asynchronous copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst and src must be 16-byte aligned and bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Same with an L2 evict-first policy: the trajectory is streamed exactly once.
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// Streaming (no L1 allocate) scalar store for write-once outputs.
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+// ---------------------------------------------------------------- minimum image, one component
+// Exactly the reference expression v -= L * rint(v / L) (mapping.py:457) with IEEE divide,
+// round-half-even and un-fused multiply/subtract.  |v| <= 0.49 L  =>  rint(v / L) == 0 and the
+// update is the identity, so the fast path is bit-identical.
+__device__ __forceinline__ float mic1(float v, float L, float thr) {
+    if (fabsf(v) > thr) {
+        float k = rintf(__fdiv_rn(v, L));
+        v = __fsub_rn(v, __fmul_rn(L, k));
+    }
+    return v;
+}
+
+}  // namespace cgb

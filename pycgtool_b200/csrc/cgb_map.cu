@@ -1,0 +1,551 @@
+// Stage 1 -- atom -> bead mapping (reference: pycgtool/mapping.py:391-463).
+//
+// K1 `map_tiles_kernel`: a segmented weighted reduction over frame-major coordinates.
+//   * The plan cuts the output beads into tiles whose atoms lie in one contiguous input span
+//     (atoms of a residue are contiguous, beads never cross residues -- mapping.py:419-425).
+//   * One CTA owns (tile, block of frames).  A producer warp streams the tile's span of every
+//     frame into shared memory with 1-D bulk asynchronous copies (TMA, `cp.async.bulk`, SASS
+//     UBLKCP) through a multi-stage mbarrier ring; every input byte is fetched from HBM once,
+//     in full 16-byte-aligned runs, with an L2 evict-first policy.
+//   * Consumer threads own one output float (bead, component) for FG frames at a time, walk the
+//     bead's atom list (slot-major ELL entries held in shared memory, loaded once per CTA),
+//     apply the reference's minimum-image update and accumulate in the reference's order, then
+//     store coalesced.
+// K1g `map_gather_kernel`: CSR gather straight from global memory, for virtual beads (which read
+//     the CG frame, mapping.py:431-438) and for beads wider than a tile.
+//
+// Bit-exactness: every floating-point step of calc_coords_weight (mapping.py:455-462) is done
+// with explicitly rounded, un-fused operations in the same order, so float32 results equal the
+// NumPy reference bit for bit.
+
+#include <algorithm>
+#include <vector>
+
+#include "cgb_common.cuh"
+
+namespace cgb {
+
+// ------------------------------------------------------------------------------------------
+// Host: plan compiler
+// ------------------------------------------------------------------------------------------
+struct TileDraft {
+    int64_t bead0 = 0;
+    int64_t nbeads = 0;
+    int64_t lo = INT64_MAX, hi = -1;
+    int32_t nslots = 0;
+};
+
+static inline int64_t entry_cap(int32_t max_span_atoms) { return std::max<int64_t>(1024, 3LL * max_span_atoms); }
+
+// Greedy left-to-right tiling; `emit(draft)` is called for every tile that computes >= 1 bead.
+template <typename Emit>
+static int tile_walk(const int32_t* bead_ptr, const int32_t* index, const uint8_t* compute, int64_t n_beads,
+                     int64_t n_atoms, int32_t max_span_atoms, int32_t max_tile_beads, Emit emit) {
+    if (!bead_ptr || (!index && bead_ptr[n_beads] > 0) || n_beads < 0 || n_atoms < 0 || max_span_atoms < 1 ||
+        max_tile_beads < 1)
+        return CGB_EINVAL;
+    const int64_t cap = entry_cap(max_span_atoms);
+    TileDraft cur;
+    cur.bead0 = 0;
+    auto flush = [&](int64_t next_bead0) {
+        if (cur.hi >= 0) emit(cur);
+        cur = TileDraft();
+        cur.bead0 = next_bead0;
+    };
+    for (int64_t b = 0; b < n_beads; ++b) {
+        const int64_t p0 = bead_ptr[b], p1 = bead_ptr[b + 1];
+        if (p1 < p0) return CGB_EINVAL;
+        const bool active = (compute == nullptr || compute[b]) && p1 > p0;
+        if (!active) {
+            // The bead keeps its output slot inside the current tile but is not computed here.
+            if (cur.nbeads + 1 > max_tile_beads || (int64_t)cur.nslots * (cur.nbeads + 1) > cap) flush(b);
+            cur.nbeads += 1;
+            continue;
+        }
+        int64_t blo = INT64_MAX, bhi = -1;
+        for (int64_t p = p0; p < p1; ++p) {
+            const int64_t a = index[p];
+            if (a < 0 || a >= n_atoms) return CGB_ERANGE;
+            blo = std::min(blo, a);
+            bhi = std::max(bhi, a);
+        }
+        const int64_t cnt = p1 - p0;
+        if (bhi - blo + 1 > max_span_atoms || cnt > cap) return CGB_ETOOBIG;
+        const int64_t nlo = std::min(cur.lo, blo), nhi = std::max(cur.hi, bhi);
+        const int64_t nsl = std::max<int64_t>(cur.nslots, cnt);
+        if (nhi - nlo + 1 > max_span_atoms || cur.nbeads + 1 > max_tile_beads || nsl * (cur.nbeads + 1) > cap) {
+            flush(b);
+            cur.lo = blo;
+            cur.hi = bhi;
+            cur.nslots = (int32_t)cnt;
+        } else {
+            cur.lo = nlo;
+            cur.hi = nhi;
+            cur.nslots = (int32_t)nsl;
+        }
+        cur.nbeads += 1;
+    }
+    flush(n_beads);
+    return CGB_OK;
+}
+
+}  // namespace cgb
+
+extern "C" int cgb_map_plan_size(const int32_t* bead_ptr, const int32_t* index, const uint8_t* compute,
+                                 int64_t n_beads, int64_t n_atoms, int32_t max_span_atoms, int32_t max_tile_beads,
+                                 int64_t* n_tiles, int64_t* n_entries, int32_t* max_span,
+                                 int32_t* max_tile_entries) {
+    if (!n_tiles || !n_entries || !max_span || !max_tile_entries) return CGB_EINVAL;
+    int64_t nt = 0, ne = 0;
+    int32_t ms = 0, me = 0;
+    int rc = cgb::tile_walk(bead_ptr, index, compute, n_beads, n_atoms, max_span_atoms, max_tile_beads,
+                            [&](const cgb::TileDraft& t) {
+                                nt += 1;
+                                const int64_t e = (int64_t)t.nslots * t.nbeads;
+                                ne += e;
+                                ms = std::max<int32_t>(ms, (int32_t)(t.hi - t.lo + 1));
+                                me = std::max<int32_t>(me, (int32_t)e);
+                            });
+    if (rc != CGB_OK) return rc;
+    *n_tiles = nt;
+    *n_entries = ne;
+    *max_span = ms;
+    *max_tile_entries = me;
+    return CGB_OK;
+}
+
+extern "C" int cgb_map_plan_build(const int32_t* bead_ptr, const int32_t* index, const void* weights,
+                                  int weights_f64, const uint8_t* compute, int64_t n_beads, int64_t n_atoms,
+                                  int32_t max_span_atoms, int32_t max_tile_beads, CgbMapTile* tiles,
+                                  CgbMapEntry* entries, double* entries_w64) {
+    if (!tiles || !entries || !weights || (weights_f64 && !entries_w64)) return CGB_EINVAL;
+    const float* w32 = static_cast<const float*>(weights);
+    const double* w64 = static_cast<const double*>(weights);
+    int64_t nt = 0, ne = 0;
+    return cgb::tile_walk(
+        bead_ptr, index, compute, n_beads, n_atoms, max_span_atoms, max_tile_beads, [&](const cgb::TileDraft& t) {
+            CgbMapTile& out = tiles[nt++];
+            out.atom0 = (int32_t)t.lo;
+            out.span = (int32_t)(t.hi - t.lo + 1);
+            out.bead0 = (int32_t)t.bead0;
+            out.nbeads = (int32_t)t.nbeads;
+            out.ent0 = ne;
+            out.nslots = t.nslots;
+            out.reserved = 0;
+            CgbMapEntry* e = entries + ne;
+            double* ew = weights_f64 ? entries_w64 + ne : nullptr;
+            for (int64_t j = 0; j < t.nbeads; ++j) {
+                const int64_t b = t.bead0 + j;
+                const int64_t p0 = bead_ptr[b], p1 = bead_ptr[b + 1];
+                const bool active = (compute == nullptr || compute[b]) && p1 > p0;
+                const int64_t cnt = active ? p1 - p0 : 0;
+                const int32_t ref3 = active ? (int32_t)(3 * (index[p0] - t.lo)) : 0;
+                for (int64_t s = 0; s < t.nslots; ++s) {
+                    CgbMapEntry& x = e[s * t.nbeads + j];
+                    if (s == 0) {
+                        x.off3 = ref3;
+                        x.bits = (int32_t)cnt;
+                        if (ew) ew[j] = 0.0;
+                    } else if (s < cnt) {
+                        x.off3 = (int32_t)(3 * (index[p0 + s] - t.lo));
+                        if (weights_f64) {
+                            x.bits = 0;
+                            ew[s * t.nbeads + j] = w64[p0 + s];
+                        } else {
+                            float wv = w32[p0 + s];
+                            x.bits = *reinterpret_cast<int32_t*>(&wv);
+                        }
+                    } else {
+                        x.off3 = ref3;  // padding: v = 0, weight = 0
+                        x.bits = 0;
+                        if (ew) ew[s * t.nbeads + j] = 0.0;
+                    }
+                }
+            }
+            ne += (int64_t)t.nslots * t.nbeads;
+        });
+}
+
+// ------------------------------------------------------------------------------------------
+// Device: K1
+// ------------------------------------------------------------------------------------------
+namespace cgb {
+
+constexpr int kMaxStages = 8;
+constexpr int kProducerThreads = 32;
+
+struct MapParams {
+    const float* xyz;
+    const float* box;  // [F][3] or nullptr
+    int64_t F, N, B;
+    const CgbMapTile* tiles;
+    const CgbMapEntry* ent;
+    const double* w64;
+    float* out;
+    int32_t k;            // frames per stage
+    int32_t nstage;       // ring depth
+    int32_t fc;           // frames per CTA
+    int32_t slot_floats;  // floats per frame slot in a stage (multiple of 4)
+    int32_t stage_floats; // floats per stage (multiple of 4)
+    int32_t ent_cap;      // entries held in shared memory
+    int32_t contiguous;   // tile == whole frame: one bulk copy per stage
+};
+
+__device__ __forceinline__ uint32_t head_floats(const float* p) {
+    return (uint32_t)((reinterpret_cast<uintptr_t>(p) & 15u) >> 2);
+}
+
+// Stage `nfl` floats starting at `src` into `slot` so that float i lands at slot[head + i].
+// Interior runs go through one bulk copy from the 16-byte-aligned address below `src`; a run that
+// would touch bytes outside [lo, hi) (only the first / last bytes of the whole array) is copied by
+// the producer warp with plain loads.  Returns the number of bytes the mbarrier must expect.
+__device__ __forceinline__ uint32_t span_bytes(const float* src, uint32_t nfl, uintptr_t lo, uintptr_t hi,
+                                               bool* edge) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uintptr_t a0 = a & ~uintptr_t(15);
+    const uintptr_t e1 = (a + 4u * (uintptr_t)nfl + 15u) & ~uintptr_t(15);
+    *edge = (a0 < lo) || (e1 > hi);
+    return *edge ? 0u : (uint32_t)(e1 - a0);
+}
+
+template <int FG, bool HAS_BOX, bool W64>
+__global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const MapParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + kMaxStages;
+    CgbMapEntry* ents = reinterpret_cast<CgbMapEntry*>(smem_raw + 128);
+    double* entw = reinterpret_cast<double*>(smem_raw + 128 + (size_t)p.ent_cap * sizeof(CgbMapEntry));
+    float* stages = reinterpret_cast<float*>(smem_raw + 128 + (size_t)p.ent_cap * sizeof(CgbMapEntry) * (W64 ? 2 : 1));
+
+    const int ncons = blockDim.x - kProducerThreads;
+    const int tid = threadIdx.x;
+    const CgbMapTile tile = p.tiles[blockIdx.x];
+    const int64_t fbeg = (int64_t)blockIdx.y * p.fc;
+    const int64_t fend = min(p.F, fbeg + p.fc);
+    const int nst = (int)((fend - fbeg + p.k - 1) / p.k);
+    const int nent = tile.nslots * tile.nbeads;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstage; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], ncons / 32);
+        }
+        fence_barrier_init();
+    }
+    // Plan entries of this tile: loaded once, reused for every frame of the CTA.
+    for (int i = tid; i < nent; i += blockDim.x) {
+        ents[i] = p.ent[tile.ent0 + i];
+        if (W64) entw[i] = p.w64[tile.ent0 + i];
+    }
+    __syncthreads();
+
+    // In contiguous mode the stage holds whole frames back to back, so the tile's atoms start
+    // 3*atom0 floats into each frame.
+    const int span_fl = 3 * tile.span;
+    const int frame_fl = p.contiguous ? (int)(3 * p.N) : p.slot_floats;
+    const int lead_fl = p.contiguous ? 3 * tile.atom0 : 0;
+
+    if (tid >= ncons) {
+        // ------------------------------------------------------------------ producer warp
+        const int lane = tid - ncons;
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(p.xyz);
+        const uintptr_t hi = lo + (uintptr_t)p.F * (uintptr_t)p.N * 12u;
+        const uint64_t policy = policy_evict_first();
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % p.nstage;
+            if (it >= p.nstage) mbar_wait(&empty[s], ((it / p.nstage) - 1) & 1);
+            const int64_t f0 = fbeg + (int64_t)it * p.k;
+            const int kk = (int)min((int64_t)p.k, fend - f0);
+            float* sbase = stages + (size_t)s * p.stage_floats;
+            const int ncopies = p.contiguous ? 1 : kk;
+            uint32_t total = 0;
+            // pass 1: edge runs by hand, and the byte count of the rest
+            for (int j = 0; j < ncopies; ++j) {
+                const float* src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
+                                                : p.xyz + ((size_t)(f0 + j) * p.N + tile.atom0) * 3;
+                const uint32_t nfl = p.contiguous ? (uint32_t)kk * (uint32_t)(3 * p.N) : (uint32_t)span_fl;
+                bool edge;
+                total += span_bytes(src, nfl, lo, hi, &edge);
+                if (edge) {
+                    float* dst = sbase + (size_t)j * p.slot_floats + head_floats(src);
+                    for (uint32_t i = lane; i < nfl; i += 32) dst[i] = __ldg(src + i);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], total);
+                for (int j = 0; j < ncopies; ++j) {
+                    const float* src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
+                                                    : p.xyz + ((size_t)(f0 + j) * p.N + tile.atom0) * 3;
+                    const uint32_t nfl = p.contiguous ? (uint32_t)kk * (uint32_t)(3 * p.N) : (uint32_t)span_fl;
+                    bool edge;
+                    const uint32_t bytes = span_bytes(src, nfl, lo, hi, &edge);
+                    if (!edge) {
+                        const void* a0 = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+                        bulk_g2s_stream(sbase + (size_t)j * p.slot_floats, a0, bytes, &full[s], policy);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int nb3 = 3 * tile.nbeads;
+    float* const outp = p.out;
+    for (int it = 0; it < nst; ++it) {
+        const int s = it % p.nstage;
+        const int64_t f0 = fbeg + (int64_t)it * p.k;
+        const int kk = (int)min((int64_t)p.k, fend - f0);
+        const float* sbase = stages + (size_t)s * p.stage_floats;
+        const int ngroups = (kk + FG - 1) / FG;
+        const int nwork = nb3 * ngroups;
+        // head of the first frame; in contiguous mode it is the head of the whole stage
+        const uint32_t h0 = head_floats(p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
+                                                     : p.xyz + ((size_t)f0 * p.N + tile.atom0) * 3);
+        mbar_wait(&full[s], (it / p.nstage) & 1);
+
+        for (int w = tid; w < nwork; w += ncons) {
+            const int g = w / nb3;
+            const int o = w - g * nb3;
+            const int jb = o / 3;
+            const int c = o - 3 * jb;
+            const CgbMapEntry e0 = ents[jb];
+            const int cnt = e0.bits;
+            if (cnt == 0) continue;
+
+            const float* base[FG];
+            float ref[FG], L[FG], thr[FG];
+            float acc[FG];
+            double accd[FG];
+            int64_t fr[FG];
+#pragma unroll
+            for (int q = 0; q < FG; ++q) {
+                const int j = min(g * FG + q, kk - 1);
+                fr[q] = f0 + j;
+                uint32_t h = h0;
+                if (!p.contiguous) h = head_floats(p.xyz + ((size_t)fr[q] * p.N + tile.atom0) * 3);
+                base[q] = sbase + (size_t)j * frame_fl + h + lead_fl + c;
+                ref[q] = base[q][e0.off3];
+                if (HAS_BOX) {
+                    L[q] = __ldg(p.box + fr[q] * 3 + c);
+                    thr[q] = 0.49f * fabsf(L[q]);
+                }
+                acc[q] = 0.0f;
+                accd[q] = 0.0;
+            }
+            for (int i = 1; i < cnt; ++i) {
+                const CgbMapEntry e = ents[i * tile.nbeads + jb];
+                const float wt = __int_as_float(e.bits);
+                double wd = 0.0;
+                if (W64) wd = entw[i * tile.nbeads + jb];
+#pragma unroll
+                for (int q = 0; q < FG; ++q) {
+                    float v = __fsub_rn(base[q][e.off3], ref[q]);
+                    if (HAS_BOX) v = mic1(v, L[q], thr[q]);
+                    if (W64)
+                        accd[q] = __dadd_rn(accd[q], __dmul_rn(wd, (double)v));
+                    else
+                        acc[q] = __fadd_rn(acc[q], __fmul_rn(wt, v));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FG; ++q) {
+                if (g * FG + q < kk) {
+                    const float r = W64 ? __double2float_rn(__dadd_rn(accd[q], (double)ref[q]))
+                                        : __fadd_rn(acc[q], ref[q]);
+                    st_stream(outp + ((size_t)fr[q] * p.B + tile.bead0) * 3 + o, r);
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Device: K1g (CSR gather from global memory)
+// ------------------------------------------------------------------------------------------
+template <bool W64>
+__global__ void __launch_bounds__(256) map_gather_kernel(const float* __restrict__ src, int64_t src_atoms,
+                                                         const float* __restrict__ box, int64_t F, int64_t B,
+                                                         const int32_t* __restrict__ bead_ptr,
+                                                         const int32_t* __restrict__ index,
+                                                         const void* __restrict__ weights,
+                                                         const int32_t* __restrict__ bead_list, int64_t n_list,
+                                                         float* __restrict__ out) {
+    const int64_t per_frame = 3 * n_list;
+    const int64_t total = F * per_frame;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = t / per_frame;
+        const int64_t r = t - f * per_frame;
+        const int64_t item = r / 3;
+        const int c = (int)(r - 3 * item);
+        const int32_t b = bead_list[item];
+        const int32_t p0 = bead_ptr[b], p1 = bead_ptr[b + 1];
+        if (p1 <= p0) continue;
+        const float* fr = src + (size_t)f * src_atoms * 3;
+        const float ref = fr[(size_t)index[p0] * 3 + c];
+        float L = 0.f, thr = 0.f;
+        if (box) {
+            L = box[f * 3 + c];
+            thr = 0.49f * fabsf(L);
+        }
+        float acc = 0.f;
+        double accd = 0.0;
+        for (int32_t q = p0 + 1; q < p1; ++q) {
+            float v = __fsub_rn(fr[(size_t)index[q] * 3 + c], ref);
+            if (box) v = mic1(v, L, thr);
+            if (W64)
+                accd = __dadd_rn(accd, __dmul_rn(static_cast<const double*>(weights)[q], (double)v));
+            else
+                acc = __fadd_rn(acc, __fmul_rn(static_cast<const float*>(weights)[q], v));
+        }
+        const float res = W64 ? __double2float_rn(__dadd_rn(accd, (double)ref)) : __fadd_rn(acc, ref);
+        out[((size_t)f * B + b) * 3 + c] = res;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host: launchers
+// ------------------------------------------------------------------------------------------
+static int g_stage_bytes = 24576;
+static int g_nstages = 4;
+static int g_frames_per_cta = 128;
+static int g_consumers = 128;
+static int g_fg = 4;
+
+template <int FG>
+static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size_t smem, bool has_box, bool w64,
+                                cudaStream_t st) {
+#define CGB_LAUNCH(HB, WD)                                                                                     \
+    do {                                                                                                       \
+        auto kern = map_tiles_kernel<FG, HB, WD>;                                                              \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e != cudaSuccess) return e;                                                                        \
+        kern<<<grid, threads, smem, st>>>(p);                                                                  \
+        return cudaGetLastError();                                                                             \
+    } while (0)
+    if (has_box && w64) CGB_LAUNCH(true, true);
+    if (has_box && !w64) CGB_LAUNCH(true, false);
+    if (!has_box && w64) CGB_LAUNCH(false, true);
+    CGB_LAUNCH(false, false);
+#undef CGB_LAUNCH
+}
+
+}  // namespace cgb
+
+extern "C" int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta) {
+    if (stage_bytes < 0 || n_stages < 0 || n_stages > cgb::kMaxStages || frames_per_cta < 0) return CGB_EINVAL;
+    cgb::g_stage_bytes = stage_bytes ? stage_bytes : 24576;
+    cgb::g_nstages = n_stages ? n_stages : 4;
+    cgb::g_frames_per_cta = frames_per_cta ? frames_per_cta : 128;
+    return CGB_OK;
+}
+
+// Extra benchmarking knobs: consumer threads per CTA (multiple of 32, <= 256) and frames per
+// register group (1, 2 or 4).
+extern "C" int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group) {
+    if (consumer_threads < 0 || consumer_threads > 256 || consumer_threads % 32) return CGB_EINVAL;
+    if (frame_group != 0 && frame_group != 1 && frame_group != 2 && frame_group != 4) return CGB_EINVAL;
+    cgb::g_consumers = consumer_threads ? consumer_threads : 128;
+    cgb::g_fg = frame_group ? frame_group : 4;
+    return CGB_OK;
+}
+
+extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms,
+                             int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries,
+                             const double* entries_w64, int32_t max_span, int32_t max_tile_entries, float* cg_xyz,
+                             void* stream) {
+    using namespace cgb;
+    if (n_frames < 0 || n_atoms < 0 || n_beads < 0 || n_tiles < 0 || max_span < 0 || max_tile_entries < 0)
+        return CGB_EINVAL;
+    if (n_frames == 0 || n_tiles == 0) return CGB_OK;
+    if (!xyz || !tiles || !entries || !cg_xyz) return CGB_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(xyz) & 3u) || (reinterpret_cast<uintptr_t>(cg_xyz) & 3u)) return CGB_EALIGN;
+    if (n_tiles > 0x7fffffffLL) return CGB_EINVAL;
+
+    MapParams p;
+    p.xyz = xyz;
+    p.box = box_len;
+    p.F = n_frames;
+    p.N = n_atoms;
+    p.B = n_beads;
+    p.tiles = tiles;
+    p.ent = entries;
+    p.w64 = entries_w64;
+    p.out = cg_xyz;
+    p.nstage = g_nstages;
+    p.ent_cap = (max_tile_entries + 1) & ~1;  // keep the float64 weight array 16-byte aligned
+    const int fg = g_fg;
+
+    // A single tile in a frame no larger than a slot: stage whole frames, one bulk copy per stage.
+    const int64_t frame_bytes = n_atoms * 12;
+    p.contiguous = (n_tiles == 1 && frame_bytes <= g_stage_bytes) ? 1 : 0;
+    if (p.contiguous) {
+        int k = (int)std::max<int64_t>(1, g_stage_bytes / std::max<int64_t>(frame_bytes, 1));
+        if (k >= fg) k -= k % fg;
+        k = (int)std::min<int64_t>(k, n_frames);
+        p.k = k;
+        p.slot_floats = 0;
+        p.stage_floats = (int)(((int64_t)k * n_atoms * 3 + 4 + 3) & ~3LL);
+    } else {
+        p.slot_floats = (3 * max_span + 4 + 3) & ~3;
+        int k = std::max(1, g_stage_bytes / (p.slot_floats * 4));
+        if (k >= fg) k -= k % fg;
+        k = (int)std::min<int64_t>(k, n_frames);
+        p.k = k;
+        p.stage_floats = k * p.slot_floats;
+    }
+    int fc = std::max(g_frames_per_cta, p.k);
+    fc -= fc % p.k;
+    p.fc = fc;
+    const int64_t nchunks = (n_frames + fc - 1) / fc;
+    if (nchunks > 65535) {
+        // grid.y limit: widen the per-CTA frame block
+        int64_t need = (n_frames + 65534) / 65535;
+        need = (need + p.k - 1) / p.k * p.k;
+        p.fc = (int)need;
+    }
+    const int64_t ny = (n_frames + p.fc - 1) / p.fc;
+
+    const size_t smem = 128 + (size_t)p.ent_cap * sizeof(CgbMapEntry) * (entries_w64 ? 2 : 1) +
+                        (size_t)p.nstage * p.stage_floats * 4;
+    if (smem > 227 * 1024) return CGB_ETOOBIG;
+    dim3 grid((unsigned)n_tiles, (unsigned)ny);
+    const int threads = g_consumers + kProducerThreads;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    const bool hb = box_len != nullptr, wd = entries_w64 != nullptr;
+    if (fg == 1)
+        e = launch_tiles<1>(p, grid, threads, smem, hb, wd, st);
+    else if (fg == 2)
+        e = launch_tiles<2>(p, grid, threads, smem, hb, wd, st);
+    else
+        e = launch_tiles<4>(p, grid, threads, smem, hb, wd, st);
+    return (int)e;
+}
+
+extern "C" int cgb_map_gather(const float* src, int64_t src_atoms, const float* box_len, int64_t n_frames,
+                              int64_t n_beads, const int32_t* bead_ptr, const int32_t* index, const void* weights,
+                              int weights_f64, const int32_t* bead_list, int64_t n_list, float* cg_xyz,
+                              void* stream) {
+    using namespace cgb;
+    if (n_frames < 0 || n_beads < 0 || n_list < 0 || src_atoms < 0) return CGB_EINVAL;
+    if (n_frames == 0 || n_list == 0) return CGB_OK;
+    if (!src || !bead_ptr || !index || !weights || !bead_list || !cg_xyz) return CGB_EINVAL;
+    const int64_t total = n_frames * n_list * 3;
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, (int64_t)kNumSMs * 32);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (weights_f64)
+        map_gather_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(src, src_atoms, box_len, n_frames, n_beads,
+                                                                     bead_ptr, index, weights, bead_list, n_list,
+                                                                     cg_xyz);
+    else
+        map_gather_kernel<false><<<(unsigned)blocks, threads, 0, st>>>(src, src_atoms, box_len, n_frames, n_beads,
+                                                                      bead_ptr, index, weights, bead_list, n_list,
+                                                                      cg_xyz);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,319 @@
+"""GPU parity of stage 2 (measurement + statistics) and stage 3 (Boltzmann inversion).
+
+Bar (north star): bond statistics and fitted parameters within 1e-4 relative of the
+reference algorithm; index assignment bit-exact (checked on CPU in test_host_logic).
+Lengths are additionally bit-exact against the oracle (same un-fused float32 ops).
+"""
+
+import json
+import math
+
+import numpy as np
+import pytest
+
+from oracle import bonds as obonds, geometry as ogeom, mapping as omap, stats as ostats, system as osystem
+from tests.helpers import oracle_system
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4            # north-star tolerance on statistics / parameters
+ANGLE_ABS = 2e-6      # float32 acos / atan2 implementations differ in the last ulps (radians)
+COS_ULPS = 4e-7       # the cosine fed to acos differs by a few float32 ulps (fused vs un-fused dot products)
+
+
+def _assert_values(bond, term, cg=None):
+    """Lengths: bit-exact.  Angles / dihedrals: float32 acos / atan2 of quantities that differ by a
+    few ulps (fused vs un-fused products), so the tolerance follows the conditioning of the term:
+    d(theta) = d(cos) / sin(theta) for angles, and for dihedrals the rounding of the cross products
+    relative to |c1||c2| (nearly collinear bead triples are ill-conditioned in any float32 kernel)."""
+    got, ref = np.asarray(bond.values), np.asarray(term.values)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    if len(term.atoms) == 2:
+        assert np.array_equal(got, ref)
+        return
+    diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    diff = np.minimum(diff, 2 * math.pi - diff)
+    tol = np.full(diff.shape, ANGLE_ABS)
+    if len(term.atoms) == 3:
+        tol = tol + COS_ULPS / np.maximum(np.sin(ref.astype(np.float64)), 1e-3)
+    elif cg is not None:
+        q = term.indices
+        b1 = ogeom.displacement(cg.xyz, q[:, 0], q[:, 1], cg.box_vectors).astype(np.float64)
+        b2 = ogeom.displacement(cg.xyz, q[:, 1], q[:, 2], cg.box_vectors).astype(np.float64)
+        b3 = ogeom.displacement(cg.xyz, q[:, 2], q[:, 3], cg.box_vectors).astype(np.float64)
+        n = lambda v: np.linalg.norm(v, axis=-1)
+        cond = n(b1) * n(b2) ** 2 * n(b3) / np.maximum(n(np.cross(b2, b3)) * n(np.cross(b1, b2)), 1e-30)
+        tol = tol + COS_ULPS * cond.reshape(-1)
+    else:
+        tol = tol * 50
+    assert (diff <= tol).all(), float((diff - tol).max())
+
+
+def _assert_params(bond, term):
+    if term.eqm is None:
+        assert bond.eqm is None and bond.fconst is None
+        return
+    assert bond.eqm == pytest.approx(term.eqm, rel=REL, abs=2e-6)
+    if math.isinf(term.fconst):
+        assert bond.fconst == math.inf
+    else:
+        assert bond.fconst == pytest.approx(term.fconst, rel=REL)
+
+
+def test_sugar_full_pipeline(golden, options):
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    cg = Mapping(golden / "sugar.map", options).apply(Frame(golden / "sugar.gro", golden / "sugar.xtc"))
+    measure = BondSet(golden / "sugar.bnd", options)
+    measure.apply(cg)
+    measure.boltzmann_invert()
+    ocg = omap.apply(omap.parse_map(golden / "sugar.map"), osystem.load(golden / "sugar.gro", golden / "sugar.xtc"))
+    terms = obonds.parse_bnd(golden / "sugar.bnd")
+    obonds.measure(terms, ocg)
+    obonds.invert(terms)
+    stored = json.loads((golden / "sugar_params.json").read_text())
+    assert len(measure["ALLA"]) == 18
+    for bond, term, row in zip(measure["ALLA"], terms["ALLA"], stored):
+        assert len(bond.values) == 1001
+        _assert_values(bond, term, ocg)
+        _assert_params(bond, term)
+        assert bond.eqm == pytest.approx(row["eqm"], rel=REL, abs=2e-6)
+        assert bond.fconst == pytest.approx(row["fconst"], rel=REL)
+        counts, edges = bond.histogram
+        expect, _ = np.histogram(np.asarray(bond.values, dtype=np.float64), bins=len(counts),
+                                 range=(float(np.float32(edges[0])), float(np.float32(edges[-1]))))
+        assert np.array_equal(counts.astype(np.int64), expect)
+
+
+def test_reference_measurement_kats(golden, options):
+    # reference tests/test_bondset.py:64-85
+    from pycgtool_b200 import BondSet, Frame
+    measure = BondSet(golden / "sugar.bnd", options)
+    measure.apply(Frame(golden / "sugar-cg.gro"))
+    b = measure["ALLA"]
+    assert len(b[0].values) == 1 and b[0].values[0] == pytest.approx(0.2225376, rel=1 / 500)
+    assert len(b[6].values) == 1 and b[6].values[0] == pytest.approx(math.radians(77.22779289), rel=1 / 500)
+    assert len(b[12].values) == 1 and b[12].values[0] == pytest.approx(math.radians(-89.5552903), rel=1 / 500)
+
+
+@pytest.mark.parametrize("column,extra", [(1, {}), (2, {"default_fc": True}),
+                                          (2, {"length_form": "MartiniDefaultLength",
+                                               "angle_form": "MartiniDefaultAngle",
+                                               "dihedral_form": "MartiniDefaultDihedral"})])
+def test_reference_boltzmann_table(golden, options, column, extra):
+    # reference tests/test_bondset.py:37-56,94-156, tolerance 0.5 %
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    table = [(0.220474419132, 72658.18163, 1250), (0.221844516963, 64300.01188, 1250),
+             (0.216313356504, 67934.93368, 1250), (0.253166204438, 19545.27388, 1250),
+             (0.205958461836, 55359.06367, 1250), (0.180550961226, 139643.66601, 1250),
+             (1.359314249473, 503.24211, 25), (2.026002746003, 837.76904, 25), (1.937848056214, 732.87969, 25),
+             (1.453592079716, 945.32633, 25), (2.504189933347, 771.63691, 25), (1.733002945619, 799.82825, 25),
+             (1.695540843207, 253.75691, 50), (-2.074156183261, 125.04591, 50), (2.768063749729, 135.50927, 50),
+             (-2.213755550432, 51.13975, 50), (1.456495664734, 59.38162, 50), (-1.826134298998, 279.80889, 50)]
+    for key, val in extra.items():
+        setattr(options, key, val)
+    measure = BondSet(golden / "sugar.bnd", options)
+    cg = Mapping(golden / "sugar.map", options).apply(Frame(golden / "sugar.gro", golden / "sugar.xtc"))
+    measure.apply(cg)
+    measure.boltzmann_invert()
+    for bond, row in zip(measure["ALLA"], table):
+        assert bond.eqm == pytest.approx(row[0], rel=5e-3)
+        assert bond.fconst == pytest.approx(row[column], rel=5e-3)
+
+
+def test_polymer_neighbour_bonds_and_pbc(golden, options):
+    # reference tests/test_bondset.py:158-182
+    from pycgtool_b200 import BondSet, Frame
+    bondset = BondSet(golden / "polyethene.bnd", options)
+    bondset.apply(Frame(golden / "polyethene.gro"))
+    assert [len(b.values) for b in bondset["ETH"]] == [5, 4, 4, 4]
+    bondset.boltzmann_invert()
+    assert bondset["ETH"][0].eqm == pytest.approx(0.107, rel=1 / 500)
+    assert bondset["ETH"][1].eqm == pytest.approx(0.107, rel=1 / 500)
+    terms = obonds.parse_bnd(golden / "polyethene.bnd")
+    obonds.measure(terms, osystem.load(golden / "polyethene.gro"))
+    obonds.invert(terms)
+    for bond, term in zip(bondset["ETH"], terms["ETH"]):
+        _assert_values(bond, term)
+    bondset = BondSet(golden / "polyethene.bnd", options)
+    bondset.apply(Frame(golden / "pbcpolyethene.gro"))
+    bondset.boltzmann_invert()
+    for bond in bondset.get_bond_lengths("ETH", True):
+        assert bond.eqm == pytest.approx(1.0)
+        assert bond.fconst == math.inf
+
+
+def test_full_itp_sugar_and_vsites(golden, options, tmp_path):
+    # reference tests/test_bondset.py:184-235 (sugar_out.itp predates circular statistics: rtol 5e-3)
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from pycgtool_b200.util import cmp_file_whitespace_float
+    measure = BondSet(golden / "sugar.bnd", options)
+    mapping = Mapping(golden / "sugar.map", options)
+    measure.apply(mapping.apply(Frame(golden / "sugar.gro", golden / "sugar.xtc")))
+    measure.boltzmann_invert()
+    measure.write_itp(tmp_path / "sugar_out.itp", mapping)
+    assert cmp_file_whitespace_float(tmp_path / "sugar_out.itp", golden / "sugar_out.itp", rtol=0.005, verbose=True)
+    options.generate_angles = False
+    measure = BondSet(golden / "martini3" / "naphthalene.bnd", options)
+    mapping = Mapping(golden / "martini3" / "naphthalene.map", options)
+    measure.apply(mapping.apply(Frame(golden / "martini3" / "naphthalene.gro")))
+    measure.boltzmann_invert()
+    measure.write_itp(tmp_path / "naphthalene_out.itp", mapping)
+    assert cmp_file_whitespace_float(tmp_path / "naphthalene_out.itp",
+                                     golden / "martini3" / "naphthalene_out.itp", rtol=0.005, verbose=True)
+
+
+def test_dump_values_vs_alla_dat(golden, options, tmp_path):
+    # reference tests/test_bondset.py:241-261
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from pycgtool_b200.util import cmp_file_whitespace_float
+    measure = BondSet(golden / "sugar.bnd", options)
+    measure.apply(Mapping(golden / "sugar.map", options).apply(Frame(golden / "sugar.gro", golden / "sugar.xtc")))
+    measure.boltzmann_invert()
+    measure.dump_values(output_dir=tmp_path)
+    for name in ("ALLA_length.dat", "ALLA_angle.dat", "ALLA_dihedral.dat"):
+        assert cmp_file_whitespace_float(golden / name, tmp_path / name, rtol=0.008, verbose=True)
+
+
+def _synthetic_bonds(sysm, n_frames, options, ortho=True, skew=None):
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    xyz = sysm.coordinates_host(n_frames)
+    box = sysm.box_vectors(n_frames)
+    if skew is not None:
+        box[:, 1, 0] = skew[0]
+        box[:, 2, 0] = skew[1]
+        box[:, 2, 1] = skew[2]
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    bondset = BondSet(bnd_path, options)
+    bondset.apply(cg)
+    bondset.boltzmann_invert()
+    ocg = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, xyz, box))
+    terms = obonds.parse_bnd(bnd_path, generate_angles=options.generate_angles,
+                             generate_dihedrals=options.generate_dihedrals)
+    obonds.measure(terms, ocg)
+    obonds.invert(terms)
+    return bondset, terms, ocg
+
+
+def test_small_molecule_chain_statistics(options):
+    """Config S3 shape (66 terms, n_inst = 1) on 4,096 frames, dihedrals straddling +-pi."""
+    from pycgtool_b200 import synth
+    bondset, terms, ocg = _synthetic_bonds(synth.small_molecule(), 4096, options)
+    assert len(bondset["MOL"]) == 66
+    for bond, term in zip(bondset["MOL"], terms["MOL"]):
+        _assert_values(bond, term, ocg)
+        _assert_params(bond, term)
+
+
+def test_membrane_many_instances_ortho_pbc(options):
+    from pycgtool_b200 import synth
+    sysm = synth.membrane(40, 60, seed=17)
+    sysm.box = np.array([4.0, 4.2, 3.9])
+    sysm.sigma = 0.12
+    options.generate_dihedrals = True
+    bondset, terms, ocg = _synthetic_bonds(sysm, 37, options)
+    for mol in ("DOPC", "POPC"):
+        assert len(bondset[mol]) == 11 + 11 + len([t for t in terms[mol] if len(t.atoms) == 4])
+        for bond, term in zip(bondset[mol], terms[mol]):
+            assert len(bond.values) == 37 * 40
+            _assert_values(bond, term, ocg)
+            _assert_params(bond, term)
+
+
+def test_triclinic_minimum_image(options):
+    from pycgtool_b200 import synth
+    sysm = synth.membrane(12, 0, seed=4)
+    sysm.box = np.array([3.0, 3.0, 3.0])
+    sysm.sigma = 0.1
+    bondset, terms, ocg = _synthetic_bonds(sysm, 11, options, skew=(0.9, -1.1, 1.3))
+    for mol in ("DOPC", "POPC"):
+        for bond, term in zip(bondset[mol], terms[mol]):
+            _assert_values(bond, term, ocg)
+            _assert_params(bond, term)
+
+
+def test_molecule_absent_and_custom_form(golden, options, tmp_path):
+    """A molecule in the .bnd that is not in the frame keeps eqm/fconst None; a user-defined
+    functional form receives the GPU statistics through the mean / variance hooks."""
+    from pycgtool_b200 import BondSet, Frame, functionalforms
+
+    class Quartic(functionalforms.FunctionalForm):
+        gromacs_type_ids = (7, 7, 7)
+
+        def fconst(self, values, temp):
+            return 2.0 / self._variance_func(values) + self._mean_func(values)
+
+    bnd = tmp_path / "x.bnd"
+    bnd.write_text((golden / "sugar.bnd").read_text() + "\n[ GHOST ]\nA B\n")
+    options.length_form = "Quartic"
+    measure = BondSet(bnd, options)
+    from pycgtool_b200 import Mapping
+    cg = Mapping(golden / "sugar.map", options).apply(Frame(golden / "sugar.gro", golden / "sugar.xtc"))
+    measure.apply(cg)
+    measure.boltzmann_invert()
+    ghost = measure["GHOST"][0]
+    assert len(ghost.values) == 0 and ghost.eqm is None and ghost.fconst is None
+    bond = measure["ALLA"][0]
+    v = np.asarray(bond.values, dtype=np.float64)
+    assert bond.gromacs_type_id == 7
+    assert bond.fconst == pytest.approx(2.0 / v.var() + v.mean(), rel=REL)
+
+
+def test_bond_level_invert_on_host_values(options):
+    """``Bond.boltzmann_invert`` on caller-supplied values (reference tests/test_functionalforms.py flow)."""
+    from pycgtool_b200.bondset import Bond
+    from pycgtool_b200.functionalforms import CosHarmonic, Harmonic
+    rng = np.random.default_rng(1)
+    lengths = rng.normal(0.3, 0.01, size=5000).astype(np.float32)
+    bond = Bond(("A", "B"), func_form=Harmonic())
+    bond.values = lengths
+    bond.boltzmann_invert(temp=300)
+    eqm, fc = ostats.boltzmann_invert(lengths, 2, "Harmonic", 300)
+    assert bond.eqm == pytest.approx(eqm, rel=REL) and bond.fconst == pytest.approx(fc, rel=REL)
+    angles = rng.normal(2.0, 0.1, size=5000).astype(np.float32)
+    bond = Bond(("A", "B", "C"), func_form=CosHarmonic())
+    bond.values = list(angles)
+    bond.boltzmann_invert()
+    eqm, fc = ostats.boltzmann_invert(angles, 3, "CosHarmonic", 310)
+    assert bond.eqm == pytest.approx(eqm, rel=REL) and bond.fconst == pytest.approx(fc, rel=REL)
+    dih = (rng.normal(3.1, 0.3, size=5000) % (2 * np.pi) - np.pi + np.pi).astype(np.float32)
+    dih = ((dih + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
+    bond = Bond(("A", "B", "C", "D"), func_form=Harmonic())
+    bond.values = dih
+    bond.boltzmann_invert()
+    eqm, fc = ostats.boltzmann_invert(dih, 4, "Harmonic", 310)
+    assert bond.eqm == pytest.approx(eqm, rel=REL, abs=2e-6) and bond.fconst == pytest.approx(fc, rel=REL)
+    empty = Bond(("A", "B"), func_form=Harmonic())
+    with pytest.raises(ValueError):
+        empty.boltzmann_invert()
+
+
+def test_frame_shards_merge_to_single_pass(options):
+    """Two frame shards measured separately and summed (what the all-reduce does) equal one pass."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, dist, synth
+    sysm = synth.small_molecule()
+    n_frames = 600
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    whole = BondSet(bnd_path, options)
+    whole.apply(mapper.apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box)))
+    shards = []
+    for rank in range(2):
+        b, e = dist.frame_shard(n_frames, rank, 2)
+        part = BondSet(bnd_path, options)
+        part.apply(mapper.apply(Frame.from_arrays(sysm.topology, xyz[b:e], unitcell_vectors=box[b:e])))
+        shards.append(part)
+    # same shift on every shard is what makes the sums addable; shard 1 re-measures with shard 0's
+    assert torch.equal(shards[0]._state.shift, whole._state.shift)
+    merged = dist.merge_partials([s._state.partials[:, :5] for s in shards]) if torch.equal(
+        shards[1]._state.shift, whole._state.shift) else None
+    counts = shards[0]._state.partials[:, 0] + shards[1]._state.partials[:, 0]
+    assert torch.equal(counts, whole._state.partials[:, 0])
+    hist = shards[0]._state.hist + shards[1]._state.hist
+    assert torch.equal(hist, whole._state.hist)
+    # circular sums do not depend on the shift and must add up to the single-pass sums
+    circ = shards[0]._state.partials[:, 3:5] + shards[1]._state.partials[:, 3:5]
+    assert torch.allclose(circ, whole._state.partials[:, 3:5], rtol=1e-12, atol=1e-9)
+    assert merged is None or torch.allclose(merged, whole._state.partials[:, :5], rtol=1e-10, atol=1e-9)

@@ -186,7 +186,8 @@ struct MapParams {
     int32_t nstage;       // ring depth
     int32_t fc;           // frames per CTA
     int32_t slot_floats;  // floats per frame slot in a stage (multiple of 4)
-    int32_t stage_floats; // floats per stage (multiple of 4)
+    int32_t stage_floats; // floats per stage (multiple of 4), box table included
+    int32_t tab_off;      // float offset of the per-frame box table inside a stage
     int32_t ent_cap;      // entries held in shared memory
     int32_t contiguous;   // tile == whole frame: one bulk copy per stage
 };
@@ -208,6 +209,191 @@ __device__ __forceinline__ uint32_t span_bytes(const float* src, uint32_t nfl, u
     return *edge ? 0u : (uint32_t)(e1 - a0);
 }
 
+// Packed float32x2 arithmetic (sm_100 FADD2): two frames per instruction, each half rounded to
+// nearest exactly like the scalar operation.  The multiply stays scalar on purpose: ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would change the reference's rounding.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// Minimum image of one component, v - L * rint(v / L) (mapping.py:457), without a division on the
+// common paths.  With t05 = the largest float32 a for which rint(fl(a / L)) == 0 (computed exactly
+// by the producer warp, see box_t05):
+//     |v| <= t05               -> rint(v / L) = 0, v unchanged
+//     t05 < |v| <= 1.49 L      -> rint(v / L) = +-1 and L * (+-1) is exact: v -= copysign(L, v)
+//     otherwise (never for whole molecules) -> the IEEE division below.
+// Each case reproduces the reference's float32 result bit for bit.
+__device__ __noinline__ float mic_divide(float v, float La) {
+    const float k = rintf(__fdiv_rn(v, La));
+    return __fsub_rn(v, __fmul_rn(La, k));
+}
+
+// t = L/2 divides to exactly 0.5, which rounds to 0 (ties to even); the next float above t may
+// still divide to 0.5 after rounding, the one after that never does.
+__device__ __forceinline__ float box_t05(float La) {
+    const float t = 0.5f * La;
+    const float t1 = __int_as_float(__float_as_int(t) + 1);
+    return (__fdiv_rn(t1, La) <= 0.5f) ? t1 : t;
+}
+
+// What a lane needs to know about its output float (bead, component); constant for the lifetime of
+// the CTA when the tile has no more 32-lane chunks than the CTA has consumer warps.
+struct LaneConst {
+    const CgbMapEntry* ep;  // slot-0 entry of the lane's bead
+    const double* wp;       // float64 weight of slot 0 (W64 only)
+    int o;                  // output float inside the tile: 3 * bead + component
+    int c4;                 // 4 * component
+    int lo;                 // byte offset of the reference atom's component inside a frame of the tile
+    int cnt;                // atoms of the bead (0: not computed here)
+    int cmax;               // max cnt over the warp (uniform loop bound; ELL padding is exact)
+};
+
+__device__ __forceinline__ LaneConst lane_const(const CgbMapTile& tile, const CgbMapEntry* ents, const double* entw,
+                                                int chunk, int lane) {
+    LaneConst k;
+    const int nb3 = 3 * tile.nbeads;
+    k.o = chunk * 32 + lane;
+    const bool valid = k.o < nb3;
+    const int oo = valid ? k.o : 0;
+    const int jb = oo / 3;
+    const int c = oo - 3 * jb;
+    k.ep = ents + jb;
+    k.wp = entw + jb;
+    const CgbMapEntry e0 = *k.ep;
+    k.cnt = valid ? e0.bits : 0;
+    k.cmax = __reduce_max_sync(0xffffffffu, k.cnt);
+    k.c4 = c * 4;
+    k.lo = e0.off3 * 4 + k.c4;
+    return k;
+}
+
+// One warp-task: the lane's output float for the FG frames of group g of the current stage.
+// g, the stage and everything derived from them are warp-uniform (frame bases live in uniform
+// registers, so the shared-memory loads are [lane offset + uniform frame base]).
+template <int FG, bool HAS_BOX, bool W64>
+__device__ __forceinline__ void map_task(const MapParams& p, const CgbMapTile& tile, const LaneConst& k,
+                                         const unsigned char* stage, int g, int kk, int64_t f0, int frame_fl,
+                                         int lead_fl, uint32_t h0b, uint32_t hstep) {
+    if (k.cmax == 0) return;
+    uint32_t base[FG];  // byte offset of the frame's tile inside the stage (warp-uniform)
+    float ref[FG], La[FG], t05[FG];
+    const float2* tab = reinterpret_cast<const float2*>(stage + (size_t)p.tab_off * 4);
+    const int c = k.c4 >> 2;
+#pragma unroll
+    for (int q = 0; q < FG; ++q) {
+        const int j = min(g * FG + q, kk - 1);
+        // 16-byte-alignment head of frame j: frames are 12 N bytes apart
+        const uint32_t h = p.contiguous ? (h0b >> 2) : (((h0b + (uint32_t)j * hstep) & 15u) >> 2);
+        base[q] = (uint32_t)(j * frame_fl + (int)h + lead_fl) * 4u;
+        ref[q] = *reinterpret_cast<const float*>(stage + base[q] + k.lo);
+        if (HAS_BOX) {
+            const float2 bt = tab[j * 3 + c];  // (|L|, t05) of this frame and component
+            La[q] = bt.x;
+            t05[q] = bt.y;
+        }
+    }
+    float thr = 0.f, rare = 0.f;
+    if (HAS_BOX) {
+        thr = t05[0];
+        rare = La[0];
+#pragma unroll
+        for (int q = 1; q < FG; ++q) {
+            thr = fminf(thr, t05[q]);
+            rare = fminf(rare, La[q]);
+        }
+        rare *= 1.49f;
+    }
+
+    float acc[FG];
+    double accd[FG];
+#pragma unroll
+    for (int q = 0; q < FG; ++q) {
+        acc[q] = 0.f;
+        accd[q] = 0.0;
+    }
+    const CgbMapEntry* ep = k.ep;
+    const double* wp = k.wp;
+    for (int i = 1; i < k.cmax; ++i) {
+        ep += tile.nbeads;
+        const CgbMapEntry e = *ep;
+        const int a = e.off3 * 4 + k.c4;
+        float v[FG];
+#pragma unroll
+        for (int q = 0; q < FG; ++q) v[q] = *reinterpret_cast<const float*>(stage + base[q] + a);
+        if (FG % 2 == 0) {
+#pragma unroll
+            for (int q = 0; q < FG; q += 2) {
+                const uint64_t d = sub2(pack2(v[q], v[q + 1]), pack2(ref[q], ref[q + 1]));
+                unpack2(d, v[q], v[q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < FG; ++q) v[q] = __fsub_rn(v[q], ref[q]);
+        }
+        if (HAS_BOX) {
+            float m = fabsf(v[0]);
+#pragma unroll
+            for (int q = 1; q < FG; ++q) m = fmaxf(m, fabsf(v[q]));
+            if (m > thr) {
+                if (m <= rare) {
+#pragma unroll
+                    for (int q = 0; q < FG; ++q)
+                        if (fabsf(v[q]) > t05[q]) v[q] = __fsub_rn(v[q], copysignf(La[q], v[q]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < FG; ++q) v[q] = mic_divide(v[q], La[q]);
+                }
+            }
+        }
+        if (W64) {
+            wp += tile.nbeads;
+            const double wd = *wp;
+#pragma unroll
+            for (int q = 0; q < FG; ++q) accd[q] = __dadd_rn(accd[q], __dmul_rn(wd, (double)v[q]));
+        } else {
+            const float wt = __int_as_float(e.bits);
+            if (FG % 2 == 0) {
+#pragma unroll
+                for (int q = 0; q < FG; q += 2) {
+                    const uint64_t s = add2(pack2(acc[q], acc[q + 1]),
+                                            pack2(__fmul_rn(wt, v[q]), __fmul_rn(wt, v[q + 1])));
+                    unpack2(s, acc[q], acc[q + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < FG; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(wt, v[q]));
+            }
+        }
+    }
+    if (k.cnt > 0) {
+        const size_t fstride = (size_t)p.B * 3;
+        float* op = p.out + ((size_t)(f0 + (int64_t)g * FG) * p.B + tile.bead0) * 3 + k.o;
+#pragma unroll
+        for (int q = 0; q < FG; ++q) {
+            if (g * FG + q < kk) {
+                const float r = W64 ? __double2float_rn(__dadd_rn(accd[q], (double)ref[q]))
+                                    : __fadd_rn(acc[q], ref[q]);
+                st_stream(op + q * fstride, r);
+            }
+        }
+    }
+}
+
 template <int FG, bool HAS_BOX, bool W64>
 __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const MapParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -219,6 +405,10 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
 
     const int ncons = blockDim.x - kProducerThreads;
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    // warp index through a shuffle so that the compiler knows it is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int ncw = ncons >> 5;
     const CgbMapTile tile = p.tiles[blockIdx.x];
     const int64_t fbeg = (int64_t)blockIdx.y * p.fc;
     const int64_t fend = min(p.F, fbeg + p.fc);
@@ -228,7 +418,7 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
     if (tid == 0) {
         for (int s = 0; s < p.nstage; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], ncons / 32);
+            mbar_init(&empty[s], ncw);
         }
         fence_barrier_init();
     }
@@ -245,9 +435,8 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
     const int frame_fl = p.contiguous ? (int)(3 * p.N) : p.slot_floats;
     const int lead_fl = p.contiguous ? 3 * tile.atom0 : 0;
 
-    if (tid >= ncons) {
+    if (warp == ncw) {
         // ------------------------------------------------------------------ producer warp
-        const int lane = tid - ncons;
         const uintptr_t lo = reinterpret_cast<uintptr_t>(p.xyz);
         const uintptr_t hi = lo + (uintptr_t)p.F * (uintptr_t)p.N * 12u;
         const uint64_t policy = policy_evict_first();
@@ -258,109 +447,76 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
             const int kk = (int)min((int64_t)p.k, fend - f0);
             float* sbase = stages + (size_t)s * p.stage_floats;
             const int ncopies = p.contiguous ? 1 : kk;
-            uint32_t total = 0;
-            // pass 1: edge runs by hand, and the byte count of the rest
-            for (int j = 0; j < ncopies; ++j) {
-                const float* src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
-                                                : p.xyz + ((size_t)(f0 + j) * p.N + tile.atom0) * 3;
-                const uint32_t nfl = p.contiguous ? (uint32_t)kk * (uint32_t)(3 * p.N) : (uint32_t)span_fl;
-                bool edge;
-                total += span_bytes(src, nfl, lo, hi, &edge);
-                if (edge) {
-                    float* dst = sbase + (size_t)j * p.slot_floats + head_floats(src);
-                    for (uint32_t i = lane; i < nfl; i += 32) dst[i] = __ldg(src + i);
+            const uint32_t nfl = p.contiguous ? (uint32_t)kk * (uint32_t)(3 * p.N) : (uint32_t)span_fl;
+            // lane j owns copy j (a stage never has more than 32 frames unless it is contiguous)
+            uint32_t bytes = 0;
+            bool edge = false;
+            const float* src = nullptr;
+            if (lane < ncopies) {
+                src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
+                                   : p.xyz + ((size_t)(f0 + lane) * p.N + tile.atom0) * 3;
+                bytes = span_bytes(src, nfl, lo, hi, &edge);
+            }
+            // runs touching the first / last bytes of the whole array are copied by hand
+            unsigned edges = __ballot_sync(0xffffffffu, edge);
+            while (edges) {
+                const int j = __ffs(edges) - 1;
+                edges &= edges - 1;
+                const float* esrc = reinterpret_cast<const float*>(
+                    __shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(src), j));
+                float* dst = sbase + (size_t)j * p.slot_floats + head_floats(esrc);
+                for (uint32_t i = lane; i < nfl; i += 32) dst[i] = __ldg(esrc + i);
+            }
+            if (HAS_BOX) {
+                // per-frame box table of the stage: (|L|, t05) for each component
+                float2* tab = reinterpret_cast<float2*>(sbase + p.tab_off);
+                for (int i = lane; i < kk * 3; i += 32) {
+                    const float La = fabsf(__ldg(p.box + f0 * 3 + i));
+                    tab[i] = make_float2(La, box_t05(La));
                 }
             }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&full[s], total);
-                for (int j = 0; j < ncopies; ++j) {
-                    const float* src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
-                                                    : p.xyz + ((size_t)(f0 + j) * p.N + tile.atom0) * 3;
-                    const uint32_t nfl = p.contiguous ? (uint32_t)kk * (uint32_t)(3 * p.N) : (uint32_t)span_fl;
-                    bool edge;
-                    const uint32_t bytes = span_bytes(src, nfl, lo, hi, &edge);
-                    if (!edge) {
-                        const void* a0 = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
-                        bulk_g2s_stream(sbase + (size_t)j * p.slot_floats, a0, bytes, &full[s], policy);
-                    }
-                }
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], total);
+            __syncwarp();
+            if (lane < ncopies && !edge) {
+                const void* a0 = reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+                bulk_g2s_stream(sbase + (size_t)lane * p.slot_floats, a0, bytes, &full[s], policy);
             }
-            __syncwarp();
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    const int nb3 = 3 * tile.nbeads;
-    float* const outp = p.out;
+    // Warp w owns the 32-lane chunks w, w + ncw, ... of the tile's output floats for every frame.
+    const int nchunks = (3 * tile.nbeads + 31) >> 5;
+    const bool resident = nchunks <= ncw;  // one chunk per warp: lane constants computed once
+    LaneConst lc = lane_const(tile, ents, entw, warp < nchunks ? warp : 0, lane);
+    const uint32_t hstep = (uint32_t)((12ull * (uint64_t)p.N) & 15ull);
     for (int it = 0; it < nst; ++it) {
         const int s = it % p.nstage;
         const int64_t f0 = fbeg + (int64_t)it * p.k;
         const int kk = (int)min((int64_t)p.k, fend - f0);
-        const float* sbase = stages + (size_t)s * p.stage_floats;
+        const unsigned char* stage = reinterpret_cast<const unsigned char*>(stages + (size_t)s * p.stage_floats);
         const int ngroups = (kk + FG - 1) / FG;
-        const int nwork = nb3 * ngroups;
-        // head of the first frame; in contiguous mode it is the head of the whole stage
-        const uint32_t h0 = head_floats(p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
-                                                     : p.xyz + ((size_t)f0 * p.N + tile.atom0) * 3);
+        // byte misalignment of the first frame's tile (of the whole stage in contiguous mode)
+        const uint32_t h0b = (uint32_t)(reinterpret_cast<uintptr_t>(
+                                 p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
+                                              : p.xyz + ((size_t)f0 * p.N + tile.atom0) * 3) & 15u);
         mbar_wait(&full[s], (it / p.nstage) & 1);
-
-        for (int w = tid; w < nwork; w += ncons) {
-            const int g = w / nb3;
-            const int o = w - g * nb3;
-            const int jb = o / 3;
-            const int c = o - 3 * jb;
-            const CgbMapEntry e0 = ents[jb];
-            const int cnt = e0.bits;
-            if (cnt == 0) continue;
-
-            const float* base[FG];
-            float ref[FG], L[FG], thr[FG];
-            float acc[FG];
-            double accd[FG];
-            int64_t fr[FG];
-#pragma unroll
-            for (int q = 0; q < FG; ++q) {
-                const int j = min(g * FG + q, kk - 1);
-                fr[q] = f0 + j;
-                uint32_t h = h0;
-                if (!p.contiguous) h = head_floats(p.xyz + ((size_t)fr[q] * p.N + tile.atom0) * 3);
-                base[q] = sbase + (size_t)j * frame_fl + h + lead_fl + c;
-                ref[q] = base[q][e0.off3];
-                if (HAS_BOX) {
-                    L[q] = __ldg(p.box + fr[q] * 3 + c);
-                    thr[q] = 0.49f * fabsf(L[q]);
-                }
-                acc[q] = 0.0f;
-                accd[q] = 0.0;
-            }
-            for (int i = 1; i < cnt; ++i) {
-                const CgbMapEntry e = ents[i * tile.nbeads + jb];
-                const float wt = __int_as_float(e.bits);
-                double wd = 0.0;
-                if (W64) wd = entw[i * tile.nbeads + jb];
-#pragma unroll
-                for (int q = 0; q < FG; ++q) {
-                    float v = __fsub_rn(base[q][e.off3], ref[q]);
-                    if (HAS_BOX) v = mic1(v, L[q], thr[q]);
-                    if (W64)
-                        accd[q] = __dadd_rn(accd[q], __dmul_rn(wd, (double)v));
-                    else
-                        acc[q] = __fadd_rn(acc[q], __fmul_rn(wt, v));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < FG; ++q) {
-                if (g * FG + q < kk) {
-                    const float r = W64 ? __double2float_rn(__dadd_rn(accd[q], (double)ref[q]))
-                                        : __fadd_rn(acc[q], ref[q]);
-                    st_stream(outp + ((size_t)fr[q] * p.B + tile.bead0) * 3 + o, r);
-                }
+        if (resident) {
+            if (warp < nchunks)
+                for (int g = 0; g < ngroups; ++g)
+                    map_task<FG, HAS_BOX, W64>(p, tile, lc, stage, g, kk, f0, frame_fl, lead_fl, h0b, hstep);
+        } else {
+            for (int chunk = warp; chunk < nchunks; chunk += ncw) {
+                lc = lane_const(tile, ents, entw, chunk, lane);
+                for (int g = 0; g < ngroups; ++g)
+                    map_task<FG, HAS_BOX, W64>(p, tile, lc, stage, g, kk, f0, frame_fl, lead_fl, h0b, hstep);
             }
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 }
 
@@ -410,11 +566,14 @@ __global__ void __launch_bounds__(256) map_gather_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // Host: launchers
 // ------------------------------------------------------------------------------------------
-static int g_stage_bytes = 24576;
-static int g_nstages = 4;
-static int g_frames_per_cta = 128;
-static int g_consumers = 128;
-static int g_fg = 4;
+// Defaults from the sweep in profiles/ (S2, B200): 32-bead tiles, 2 stages of <= 24 KB and 3
+// consumer warps give five CTAs (15 consumer warps, ~90 KB of loads in flight) per SM.
+constexpr int kDefStageBytes = 24576, kDefStages = 2, kDefFramesPerCta = 128, kDefConsumers = 96, kDefFg = 4;
+static int g_stage_bytes = kDefStageBytes;
+static int g_nstages = kDefStages;
+static int g_frames_per_cta = kDefFramesPerCta;
+static int g_consumers = kDefConsumers;
+static int g_fg = kDefFg;
 
 template <int FG>
 static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size_t smem, bool has_box, bool w64,
@@ -438,9 +597,9 @@ static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size
 
 extern "C" int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta) {
     if (stage_bytes < 0 || n_stages < 0 || n_stages > cgb::kMaxStages || frames_per_cta < 0) return CGB_EINVAL;
-    cgb::g_stage_bytes = stage_bytes ? stage_bytes : 24576;
-    cgb::g_nstages = n_stages ? n_stages : 4;
-    cgb::g_frames_per_cta = frames_per_cta ? frames_per_cta : 128;
+    cgb::g_stage_bytes = stage_bytes ? stage_bytes : cgb::kDefStageBytes;
+    cgb::g_nstages = n_stages ? n_stages : cgb::kDefStages;
+    cgb::g_frames_per_cta = frames_per_cta ? frames_per_cta : cgb::kDefFramesPerCta;
     return CGB_OK;
 }
 
@@ -449,8 +608,8 @@ extern "C" int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t
 extern "C" int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group) {
     if (consumer_threads < 0 || consumer_threads > 256 || consumer_threads % 32) return CGB_EINVAL;
     if (frame_group != 0 && frame_group != 1 && frame_group != 2 && frame_group != 4) return CGB_EINVAL;
-    cgb::g_consumers = consumer_threads ? consumer_threads : 128;
-    cgb::g_fg = frame_group ? frame_group : 4;
+    cgb::g_consumers = consumer_threads ? consumer_threads : cgb::kDefConsumers;
+    cgb::g_fg = frame_group ? frame_group : cgb::kDefFg;
     return CGB_OK;
 }
 
@@ -489,14 +648,16 @@ extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_f
         k = (int)std::min<int64_t>(k, n_frames);
         p.k = k;
         p.slot_floats = 0;
-        p.stage_floats = (int)(((int64_t)k * n_atoms * 3 + 4 + 3) & ~3LL);
+        p.tab_off = (int)(((int64_t)k * n_atoms * 3 + 8 + 3) & ~3LL);
+        p.stage_floats = p.tab_off + ((6 * k + 3) & ~3);
     } else {
-        p.slot_floats = (3 * max_span + 4 + 3) & ~3;
-        int k = std::max(1, g_stage_bytes / (p.slot_floats * 4));
+        p.slot_floats = (3 * max_span + 8 + 3) & ~3;
+        int k = std::min(32, std::max(1, g_stage_bytes / (p.slot_floats * 4)));
         if (k >= fg) k -= k % fg;
         k = (int)std::min<int64_t>(k, n_frames);
         p.k = k;
-        p.stage_floats = k * p.slot_floats;
+        p.tab_off = k * p.slot_floats;
+        p.stage_floats = p.tab_off + ((6 * k + 3) & ~3);
     }
     int fc = std::max(g_frames_per_cta, p.k);
     fc -= fc % p.k;

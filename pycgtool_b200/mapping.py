@@ -23,9 +23,10 @@ from .topology import Topology
 
 logger = logging.getLogger(__name__)
 
-#: widest input span (atoms) one shared-memory tile may stage, and most beads per tile
+#: widest input span (atoms) one shared-memory tile may stage, and most beads per tile.
+#: 32 beads = 96 output floats = three full warps of (bead, component) lanes per frame group.
 MAX_SPAN_ATOMS = 512
-MAX_TILE_BEADS = 512
+MAX_TILE_BEADS = 32
 #: host-resident inputs at least this large are streamed through the GPU in frame chunks
 STREAM_THRESHOLD_BYTES = 512 << 20
 

@@ -10,7 +10,7 @@ NumPy:
 
 * no unit cell -> plain differences;
 * unit cell with all angles ~ 90 deg (``np.allclose``) -> orthorhombic minimum
-  image ``r -= L * round(r / L)`` with the box diagonal;
+  image ``r -= L * round(r * (1 / L))`` with the box diagonal (the C kernel's form);
 * otherwise triclinic: reduce the box vectors, subtract rounded multiples of
   c, b, a, then take the shortest of the 27 neighbouring images.
 
@@ -53,8 +53,11 @@ def displacement(xyz, i, j, box=None):
     if box is None:
         return r
     if is_orthorhombic(box):
+        # mdtraj's C kernel multiplies by the float32 inverse box length instead of dividing
+        # (distancekernel.h: r12 -= round(r12 * inv_box_size) * box_size).
         length = np.stack([box[:, 0, 0], box[:, 1, 1], box[:, 2, 2]], axis=1).astype(F32)[:, None, :]
-        return (r - length * np.round(r / length)).astype(F32)
+        inverse = (F32(1.0) / length).astype(F32)
+        return (r - length * np.round((r * inverse).astype(F32))).astype(F32)
     a, b, c = _reduced_box(box)
     a, b, c = a[:, None, :], b[:, None, :], c[:, None, :]
     r = r - c * np.round(r[..., 2:3] / c[..., 2:3])

@@ -491,10 +491,22 @@ class BondSet:
         reference stores (fetched lazily), and the statistics accumulators needed by
         ``boltzmann_invert`` are already on the device.
         """
+        import os
+        import time
         import torch
         device.require_cuda()
         lib = _lib.load()
+        trace = os.environ.get("CGB_TRACE")
+        marks = [("start", time.perf_counter())]
+
+        def mark(label):
+            if trace:
+                torch.cuda.synchronize()
+                marks.append((label, time.perf_counter()))
+
+        self._state = None          # release the previous call's buffers before allocating new ones
         plan = self._plan_for(frame._topology)
+        mark("plan")
         traj = frame._trajectory
         xyz = traj.device_xyz()
         dev = xyz.device
@@ -502,25 +514,27 @@ class BondSet:
         n2, n3, n4 = plan.counts
         n_cols = n2 + n3 + n4
         d = self._device_plan(plan, dev)
-        d["forms"] = device.to_device(self._form_ids(), dev)
+        if "forms" not in d:
+            d["forms"] = device.to_device(self._form_ids(), dev)
 
-        box = traj.unitcell_vectors
-        box_dev, ortho = None, 1
-        if box is not None:
-            # mdtraj: orthorhombic fast path only if every angle of every frame is ~90 degrees
-            ortho = int(np.allclose(traj.unitcell_angles, 90))
-            box_dev = device.to_device(box.reshape(n_frames, 9), dev, dtype=np.float32)
+        # mdtraj: orthorhombic fast path only if every angle of every frame is ~90 degrees
+        box_dev, ortho = traj.device_box_vectors(dev), int(traj.orthorhombic)
+        mark("box")
 
         values = torch.empty((n_frames, n_cols), dtype=torch.float32, device=dev)
         partials = torch.zeros((plan.n_bonds, _lib.NPART), dtype=torch.float64, device=dev)
-        hist = hist_lo = hist_hi = None
+        hist = hist_lo = hist_hi = lo = hi = None
         if histogram and plan.n_bonds:
             nbins = int(self.histogram_bins)
             hist = torch.zeros((plan.n_bonds, nbins), dtype=torch.int64, device=dev)
-            lo = np.array([self.histogram_ranges[int(k)][0] for k in plan.natoms], dtype=np.float32)
-            hi = np.array([self.histogram_ranges[int(k)][1] for k in plan.natoms], dtype=np.float32)
-            hist_lo, hist_hi = device.to_device(lo, dev), device.to_device(hi, dev)
+            key = ("hist", tuple(sorted(self.histogram_ranges.items())))
+            if key not in d:
+                lo = np.array([self.histogram_ranges[int(k)][0] for k in plan.natoms], dtype=np.float32)
+                hi = np.array([self.histogram_ranges[int(k)][1] for k in plan.natoms], dtype=np.float32)
+                d[key] = (lo, hi, device.to_device(lo, dev), device.to_device(hi, dev))
+            lo, hi, hist_lo, hist_hi = d[key]
         stream = device.stream_handle()
+        mark("alloc")
 
         def measure(nf, vals, parts, shift, hst):
             _lib.check(lib.cgb_measure(device.dptr(xyz), device.dptr(box_dev), ortho, nf, plan.n_beads,
@@ -535,13 +549,18 @@ class BondSet:
         if n_cols and n_frames:
             scratch = torch.zeros_like(partials)
             measure(1, values, scratch, None, None)
-            first_col = np.array([cols[0] if len(cols) else 0 for cols in plan.bond_cols], dtype=np.int64)
-            has = torch.from_numpy(np.array([len(cols) > 0 for cols in plan.bond_cols])).to(dev)
-            picked = values[0].index_select(0, torch.from_numpy(first_col).to(dev))
+            if "first_col" not in d:
+                first_col = np.array([cols[0] if len(cols) else 0 for cols in plan.bond_cols], dtype=np.int64)
+                d["first_col"] = device.to_device(first_col, dev)
+                d["has_col"] = device.to_device(np.array([len(cols) > 0 for cols in plan.bond_cols]), dev)
+            has = d["has_col"]
+            picked = values[0].index_select(0, d["first_col"])
             shift = torch.where(has & torch.isfinite(picked), picked, torch.zeros_like(picked)).contiguous()
         dist.broadcast(shift, src=0)
+        mark("shift")
         if n_cols and n_frames:
             measure(n_frames, values, partials, shift, hist)
+        mark("measure")
 
         self._state = _MeasureState(self, plan, n_frames, values, partials, hist, shift,
                                     None if hist is None else lo, None if hist is None else hi, dev)
@@ -549,6 +568,9 @@ class BondSet:
             bond._values = None
             bond._source = (self._state, bond_id)
             bond.eqm = bond.fconst = None
+        if trace:
+            print("BondSet.apply trace:", ", ".join(
+                f"{label} {1e3 * (t - marks[i][1]):.2f} ms" for i, (label, t) in enumerate(marks[1:])))
 
     def boltzmann_invert(self):
         """Equilibrium values and force constants of all bonds (``bondset.py:533-539``)."""

@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(256) map_gather_kernel(const float* __restrict
 // consumer warps give five CTAs (15 consumer warps, ~90 KB of loads in flight) per SM.
 constexpr int kDefStageBytes = 24576, kDefStages = 2, kDefFramesPerCta = 128, kDefConsumers = 96, kDefFg = 4;
 static int g_stage_bytes = kDefStageBytes;
+static int g_stage_user = 0;  // stage size was set explicitly through cgb_map_set_tuning
 static int g_nstages = kDefStages;
 static int g_frames_per_cta = kDefFramesPerCta;
 static int g_consumers = kDefConsumers;
@@ -598,6 +599,7 @@ static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size
 extern "C" int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta) {
     if (stage_bytes < 0 || n_stages < 0 || n_stages > cgb::kMaxStages || frames_per_cta < 0) return CGB_EINVAL;
     cgb::g_stage_bytes = stage_bytes ? stage_bytes : cgb::kDefStageBytes;
+    cgb::g_stage_user = stage_bytes ? 1 : 0;
     cgb::g_nstages = n_stages ? n_stages : cgb::kDefStages;
     cgb::g_frames_per_cta = frames_per_cta ? frames_per_cta : cgb::kDefFramesPerCta;
     return CGB_OK;
@@ -640,12 +642,14 @@ extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_f
     const int fg = g_fg;
 
     // A single tile in a frame no larger than a slot: stage whole frames, one bulk copy per stage.
+    // Small stages keep many CTAs resident (the sweep under profiles/ favours ~12 KB there).
     const int64_t frame_bytes = n_atoms * 12;
-    p.contiguous = (n_tiles == 1 && frame_bytes <= g_stage_bytes) ? 1 : 0;
+    p.contiguous = (n_tiles == 1 && frame_bytes * fg <= g_stage_bytes) ? 1 : 0;
     if (p.contiguous) {
-        int k = (int)std::max<int64_t>(1, g_stage_bytes / std::max<int64_t>(frame_bytes, 1));
-        if (k >= fg) k -= k % fg;
-        k = (int)std::min<int64_t>(k, n_frames);
+        const int64_t budget = g_stage_user ? g_stage_bytes : g_stage_bytes / 2;
+        int k = (int)std::max<int64_t>(fg, budget / std::max<int64_t>(frame_bytes, 1));
+        k -= k % fg;
+        k = (int)std::min<int64_t>(k, std::max<int64_t>(n_frames, 1));
         p.k = k;
         p.slot_floats = 0;
         p.tab_off = (int)(((int64_t)k * n_atoms * 3 + 8 + 3) & ~3LL);

@@ -322,6 +322,27 @@ class Trajectory:
             self._xyz_dev = dev.to_device(self._xyz, device)
         return self._xyz_dev
 
+    def device_box_vectors(self, device):
+        """(F, 9) float32 box vectors on the device (uploaded once), or None without a unit cell."""
+        if self._vectors is None:
+            return None
+        cached = getattr(self, "_vectors_dev", None)
+        if cached is None or cached.device != device:
+            from . import device as dev
+            cached = dev.to_device(self._vectors.reshape(self.n_frames, 9), device, dtype=np.float32)
+            self._vectors_dev = cached
+        return cached
+
+    @property
+    def orthorhombic(self):
+        """mdtraj's test for the orthorhombic minimum-image fast path: every unit-cell angle of
+        every frame is close to 90 degrees (``np.allclose``); evaluated once."""
+        if self._vectors is None:
+            return True
+        if getattr(self, "_ortho", None) is None:
+            self._ortho = bool(np.allclose(self.unitcell_angles, 90))
+        return self._ortho
+
     # ---- unit cell
     @property
     def unitcell_vectors(self):
@@ -331,6 +352,8 @@ class Trajectory:
     def unitcell_vectors(self, vectors):
         if vectors is None or not np.any(vectors):
             self._vectors = None
+            self._vectors_dev = None
+            self._ortho = None
             self.unitcell_lengths = None
             self.unitcell_angles = None
             return
@@ -338,6 +361,8 @@ class Trajectory:
         if vectors.shape != (self.n_frames, 3, 3):
             raise TypeError("unitcell_vectors must have shape (n_frames, 3, 3)")
         self._vectors = vectors
+        self._vectors_dev = None
+        self._ortho = None
         self.unitcell_lengths, self.unitcell_angles = lengths_and_angles(vectors)
 
     def slice(self, key):

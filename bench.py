@@ -329,11 +329,21 @@ def run_b200(args):
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        # nvidia-smi samples every 100 ms and the K timed steps last tens of ms: run the same step
+        # under the sampler before and after the timed region so that the load is actually observed
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.6:
+            step()
+            torch.cuda.synchronize()
         start.record()
         for _ in range(args.steps):
             step()
         stop.record()
         torch.cuda.synchronize()
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.6:
+            step()
+            torch.cuda.synchronize()
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()
@@ -354,12 +364,15 @@ def run_b200(args):
                 "traffic": None, "kernel": "cgb::map_tiles_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+    # DRAM traffic of one K1 launch from the committed ncu capture (dram__bytes_read.sum + write.sum),
+    # recorded per frame of this workload so that it scales to the frame count of this run
     traffic_file = ROOT / "profiles" / "k1_traffic.json"
     if traffic_file.exists():
         try:
             tr = json.loads(traffic_file.read_text())
-            if tr.get("workload") == args.workload and tr.get("frames") == frames:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
+            if tr.get("workload") == args.workload:
+                roofline["traffic"] = tr["dram_bytes_per_frame"] * frames
+                roofline["traffic_source"] = tr.get("source")
         except (ValueError, KeyError):
             pass
 
@@ -397,6 +410,7 @@ def run_b200(args):
         del host, frame, cg
 
     clock_info = clocks.summary()
+    clock_info["window"] = "0.6 s of identical steps + the timed steps + 0.6 s of identical steps, 100 ms sampling"
     line = {
         "metric": "atom-frames/s", "value": value, "unit": "atom-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,

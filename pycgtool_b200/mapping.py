@@ -15,7 +15,7 @@ import logging
 
 import numpy as np
 
-from . import _lib, device, formats
+from . import _lib, device, dist, formats
 from .elements import mass_by_symbol
 from .frame import Frame
 from .parsers import CFG, ITP
@@ -532,7 +532,8 @@ class Mapping:
         traj = frame._trajectory
         # mapping.py:406-408: lengths only, and no PBC at all if any length of any frame is zero
         box = frame.unitcell_lengths
-        if box is not None and not np.all(box):
+        # evaluated over the whole trajectory, i.e. over every frame shard when sharded across GPUs
+        if not dist.all_true(box is not None and bool(np.all(box)), device=device.default_device()):
             box = None
         host_xyz = None
         if not traj.on_device and traj.xyz.nbytes >= STREAM_THRESHOLD_BYTES and plan.n_beads:

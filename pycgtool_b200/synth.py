@@ -53,6 +53,7 @@ class SyntheticSystem:
     def write_files(self, directory=None):
         """Write the .map / .bnd pair; returns their paths."""
         directory = pathlib.Path(directory or tempfile.mkdtemp(prefix="cgb_synth_"))
+        directory.mkdir(parents=True, exist_ok=True)
         map_path, bnd_path = directory / f"{self.name}.map", directory / f"{self.name}.bnd"
         map_path.write_text(self.map_text)
         bnd_path.write_text(self.bnd_text)
@@ -90,22 +91,32 @@ class SyntheticSystem:
             out[k] = np.mod(pos, length).astype(np.float32)
         return out
 
-    def coordinates_device(self, n_frames, device, first_frame=0, chunk=64):
+    def coordinates_device(self, n_frames, device, first_frame=0, chunk=None):
         """(F, N, 3) float32 CUDA tensor, generated on the device in frame chunks."""
         import torch
         top = self.topology
+        if chunk is None:
+            # ~256 MB of coordinates per chunk, a power of two that depends on the system only
+            chunk = 1
+            while chunk < 16384 and 2 * chunk * top.n_atoms * 12 <= (256 << 20):
+                chunk *= 2
         gen = torch.Generator(device=device)
         res_len = torch.from_numpy(np.diff(top.res_first)).to(device)
         res_first = torch.from_numpy(top.res_first[:-1].copy()).to(device)
-        box = torch.from_numpy(self.box_vectors(n_frames, first_frame)).to(device)
-        length = torch.stack([box[:, 0, 0], box[:, 1, 1], box[:, 2, 2]], dim=1)        # (F, 3)
         out = torch.empty((n_frames, top.n_atoms, 3), dtype=torch.float32, device=device)
         res_of_atom = torch.repeat_interleave(torch.arange(top.n_residues, device=device), res_len)
-        for f0 in range(0, n_frames, chunk):
-            f1 = min(n_frames, f0 + chunk)
-            gen.manual_seed(self.seed * 1000003 + first_frame + f0)
-            n = f1 - f0
-            centres = torch.rand((n, top.n_residues, 3), generator=gen, device=device) * length[f0:f1, None, :]
+        # Frames are generated in absolute chunks [c*chunk, (c+1)*chunk) seeded by c, so that any
+        # frame shard (first_frame, n_frames) sees exactly the coordinates of the whole trajectory.
+        last = first_frame + n_frames
+        for c in range(first_frame // chunk, (last + chunk - 1) // chunk):
+            a0 = c * chunk                                   # absolute first frame of the chunk
+            lo, hi = max(a0, first_frame), min(a0 + chunk, last)
+            gen.manual_seed(self.seed * 1000003 + c)
+            n = chunk
+            rng = np.random.default_rng(self.seed + 7919)
+            jitter = rng.uniform(0.99, 1.01, size=(a0 + chunk, 3))[a0:]
+            clen = torch.from_numpy((self.box[None, :] * jitter).astype(np.float32)).to(device)   # (chunk, 3)
+            centres = torch.rand((n, top.n_residues, 3), generator=gen, device=device) * clen[:, None, :]
             if self.chain:
                 steps = torch.randn((n, top.n_atoms, 3), generator=gen, device=device)
                 steps = steps / steps.norm(dim=2, keepdim=True)
@@ -116,7 +127,8 @@ class SyntheticSystem:
             else:
                 pos = centres[:, res_of_atom] + self.sigma * torch.randn(
                     (n, top.n_atoms, 3), generator=gen, device=device)
-            out[f0:f1] = torch.remainder(pos, length[f0:f1, None, :])
+            pos = torch.remainder(pos, clen[:, None, :])
+            out[lo - first_frame:hi - first_frame] = pos[lo - a0:hi - a0]
             del centres, pos
         return out
 

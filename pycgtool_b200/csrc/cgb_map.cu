@@ -230,6 +230,22 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// Packed product rounded to nearest, written as fma(a, b, +0) so that ptxas has no multiply to
+// contract with the add that follows (it folds mul.rn.f32x2 -- and even fma(a, b, -0) -- plus
+// add.rn.f32x2 into one FFMA2, which changes the rounding).  fma(a, b, +0) equals rn(a * b) except
+// that a product of -0 becomes +0; the accumulator it is added to starts at +0 and can never be -0,
+// so acc + (+0) == acc + (-0) and the sum is bit-identical to the reference's.
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    const uint64_t poszero2 = 0x0000000000000000ull;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(poszero2));
+    return r;
+}
 
 // Minimum image of one component, v - L * rint(v / L) (mapping.py:457), without a division on the
 // common paths.  With t05 = the largest float32 a for which rint(fl(a / L)) == 0 (computed exactly
@@ -307,20 +323,17 @@ __device__ __forceinline__ void map_task(const MapParams& p, const CgbMapTile& t
             t05[q] = bt.y;
         }
     }
-    float thr = 0.f, rare = 0.f;
+    float rare = 0.f;
     if (HAS_BOX) {
-        thr = t05[0];
         rare = La[0];
 #pragma unroll
-        for (int q = 1; q < FG; ++q) {
-            thr = fminf(thr, t05[q]);
-            rare = fminf(rare, La[q]);
-        }
+        for (int q = 1; q < FG; ++q) rare = fminf(rare, La[q]);
         rare *= 1.49f;
     }
 
     float acc[FG];
     double accd[FG];
+    float vmax = 0.f;
 #pragma unroll
     for (int q = 0; q < FG; ++q) {
         acc[q] = 0.f;
@@ -346,18 +359,26 @@ __device__ __forceinline__ void map_task(const MapParams& p, const CgbMapTile& t
             for (int q = 0; q < FG; ++q) v[q] = __fsub_rn(v[q], ref[q]);
         }
         if (HAS_BOX) {
-            float m = fabsf(v[0]);
+            // common cases without a branch: v += t * copysign(|L|, -v) with t = (|v| > t05) ? 1 : 0.
+            // t * |L| is exact, so the fused form rounds once, exactly like v - L * rint(v / L); the
+            // running maximum decides after the loop whether any |v| was beyond 1.49 |L|.
+            float t[FG], sh[FG];
 #pragma unroll
-            for (int q = 1; q < FG; ++q) m = fmaxf(m, fabsf(v[q]));
-            if (m > thr) {
-                if (m <= rare) {
+            for (int q = 0; q < FG; ++q) {
+                vmax = fmaxf(vmax, fabsf(v[q]));
+                t[q] = fabsf(v[q]) > t05[q] ? 1.f : 0.f;
+                // |L| with the sign opposite to v, as one three-input logic op
+                sh[q] = __int_as_float((__float_as_int(La[q]) & 0x7fffffff) | (~__float_as_int(v[q]) & 0x80000000));
+            }
+            if (FG % 2 == 0) {
 #pragma unroll
-                    for (int q = 0; q < FG; ++q)
-                        if (fabsf(v[q]) > t05[q]) v[q] = __fsub_rn(v[q], copysignf(La[q], v[q]));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < FG; ++q) v[q] = mic_divide(v[q], La[q]);
+                for (int q = 0; q < FG; q += 2) {
+                    const uint64_t r = fma2(pack2(t[q], t[q + 1]), pack2(sh[q], sh[q + 1]), pack2(v[q], v[q + 1]));
+                    unpack2(r, v[q], v[q + 1]);
                 }
+            } else {
+#pragma unroll
+                for (int q = 0; q < FG; ++q) v[q] = __fmaf_rn(t[q], sh[q], v[q]);
             }
         }
         if (W64) {
@@ -368,15 +389,41 @@ __device__ __forceinline__ void map_task(const MapParams& p, const CgbMapTile& t
         } else {
             const float wt = __int_as_float(e.bits);
             if (FG % 2 == 0) {
+                const uint64_t w2 = pack2(wt, wt);
 #pragma unroll
                 for (int q = 0; q < FG; q += 2) {
-                    const uint64_t s = add2(pack2(acc[q], acc[q + 1]),
-                                            pack2(__fmul_rn(wt, v[q]), __fmul_rn(wt, v[q + 1])));
+                    const uint64_t s = add2(pack2(acc[q], acc[q + 1]), mul2(w2, pack2(v[q], v[q + 1])));
                     unpack2(s, acc[q], acc[q + 1]);
                 }
             } else {
 #pragma unroll
                 for (int q = 0; q < FG; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(wt, v[q]));
+            }
+        }
+    }
+    if (HAS_BOX && __any_sync(0xffffffffu, vmax > rare)) {
+        // some |v| reached 1.49 |L| (atoms of one bead more than a box apart): redo the task with the
+        // general IEEE-division minimum image.  Never taken for whole or wrapped molecules.
+#pragma unroll
+        for (int q = 0; q < FG; ++q) {
+            acc[q] = 0.f;
+            accd[q] = 0.0;
+        }
+        ep = k.ep;
+        wp = k.wp;
+        for (int i = 1; i < k.cmax; ++i) {
+            ep += tile.nbeads;
+            wp += tile.nbeads;
+            const CgbMapEntry e = *ep;
+            const int a = e.off3 * 4 + k.c4;
+#pragma unroll
+            for (int q = 0; q < FG; ++q) {
+                float v = __fsub_rn(*reinterpret_cast<const float*>(stage + base[q] + a), ref[q]);
+                v = mic_divide(v, La[q]);
+                if (W64)
+                    accd[q] = __dadd_rn(accd[q], __dmul_rn(*wp, (double)v));
+                else
+                    acc[q] = __fadd_rn(acc[q], __fmul_rn(__int_as_float(e.bits), v));
             }
         }
     }

@@ -117,7 +117,9 @@ int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
  * A "column" is one instance of one bonded term (bondset.py:509-528); columns are ordered lengths,
  * then angles, then dihedrals (n2, n3, n4 of them).  col_beads: device int32 [M][4] bead indices
  * (unused trailing entries repeat the last bead); col_bond: device int32 [M] owning Bond.
- * values: device float32 [F][M] (frame-major; Bond.values = values[:, cols of the bond].flatten()).
+ * values: device float32, F*M floats stored as one plane per kind, planes in kind order: the plane of a
+ * kind with n columns starting at column c0 begins at float F*c0 and is [F][n] frame-major
+ * (Bond.values = plane[:, columns of the bond].flatten()); each kernel then writes one contiguous region.
  *   length   |mic(x1 - x0)|                                         (mdtraj compute_distances)
  *   angle    acos(u.v / |u||v|), u = mic(x0 - x1), v = mic(x2 - x1)  (mdtraj compute_angles)
  *   dihedral atan2((b1.c1)|b2|, c1.c2), b_i = mic(x_i - x_{i-1}), c1 = b2 x b3, c2 = b1 x b2
@@ -135,19 +137,32 @@ int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
  * linspace(hist_lo[b], hist_hi[b], n_bins + 1) with numpy.histogram's edge rules.
  * ---------------------------------------------------------------------------------------------- */
 #define CGB_NPART 8
+/* col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one
+ * kind (a kind with fewer columns is one group) the distinct Bonds are numbered 0, 1, ... in any order and
+ * col_slot[c] is the number of column c's Bond; max_slots is the largest count over all groups.  It lets a
+ * CTA keep its per-Bond sums and histograms in shared memory sized by the group, not by the system.
+ * NULL (or max_slots too large for shared memory) selects global atomics. */
+#define CGB_MEASURE_TILE 256
+/* tile_span: device int32 [T][2] or NULL, T = sum over kinds of ceil(n_kind / CGB_MEASURE_TILE), one row per
+ * group in kind order: (first bead, number of beads) of the contiguous bead range that contains every bead
+ * of the group's columns; max_span = the largest number of beads.  With tile_span (and col_slot) the staged
+ * kernels run: the range is streamed through shared memory with bulk copies and gathered with LDS.  NULL, or
+ * a range too large for shared memory, selects the kernels that gather from global memory. */
 
 int cgb_measure(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
-                const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
+                const int32_t* col_beads, const int32_t* col_bond, const int32_t* col_slot, int32_t max_slots,
+                const int32_t* tile_span, int32_t max_span, int64_t n2, int64_t n3, int64_t n4,
                 int64_t n_bonds, const float* shift, float* values, double* partials,
                 unsigned long long* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
                 void* stream);
 
 /* Pass 2 for dihedral columns: partials[b][5] += sum over the bond's values of wrap(v - m_b)^2 with
  * m_b = atan2(partials[b][4], partials[b][3]) (util.py:40-53).  Call after partials[.][3..4] are final
- * (i.e. after the cross-GPU reduction).  Columns [col_begin, col_begin + n_cols) of `values` are read. */
-int cgb_circular_pass2(const float* values, int64_t n_frames, int64_t n_cols_total,
-                       const int32_t* col_bond, int64_t col_begin, int64_t n_cols,
-                       double* partials, void* stream);
+ * (i.e. after the cross-GPU reduction).  values: device pointer to the first of n_cols columns of a
+ * [F][row_stride] matrix (the dihedral plane: values + F*(n2+n3), row_stride = n4); col_bond: the Bond of
+ * each of those columns (col_bond + n2 + n3). */
+int cgb_circular_pass2(const float* values, int64_t n_frames, int64_t row_stride,
+                       const int32_t* col_bond, int64_t n_cols, double* partials, void* stream);
 
 /* Statistics of a caller-supplied value array for ONE Bond (Bond.boltzmann_invert on values that were
  * not measured by cgb_measure, bondset.py:72-74): accumulates slots [0..4] and [6] of one partials row.

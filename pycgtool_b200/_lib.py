@@ -11,6 +11,7 @@ _CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIBRARY_PATH = _CSRC / "libpycgtool_b200.so"
 
 NPART = 8  # CGB_NPART
+MEASURE_TILE = 256  # CGB_MEASURE_TILE
 
 FORM_IDS = {
     "Harmonic": 0,
@@ -49,9 +50,9 @@ SIGNATURES = {
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "cgb_map_set_tuning": (_int, [_i32, _i32, _i32]),
     "cgb_map_set_shape": (_int, [_i32, _i32]),
-    "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
-                           _vp, _vp, _vp, _i32, _vp]),
-    "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64,
+                           _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "cgb_value_stats": (_int, [_vp, _i64, _int, ctypes.c_float, _vp, _vp]),
     "cgb_boltzmann": (_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _i64, _vp, _vp]),
 }

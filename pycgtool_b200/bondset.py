@@ -125,7 +125,7 @@ def _stats_of_values(values, natoms):
                "cgb_value_stats")
     if natoms == 4:
         zero = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.check(lib.cgb_circular_pass2(device.dptr(vals), len(values), 1, device.dptr(zero), 0, 1,
+        _lib.check(lib.cgb_circular_pass2(device.dptr(vals), len(values), 1, device.dptr(zero), 1,
                                           device.dptr(row), stream), "cgb_circular_pass2")
     out = torch.empty(4, dtype=torch.float64, device=dev)
     nat = torch.tensor([natoms], dtype=torch.int32, device=dev)
@@ -146,6 +146,10 @@ class MeasurePlan:
         self.counts = (0, 0, 0)       # columns per kind (lengths, angles, dihedrals)
         self.col_beads = None         # int32 (M, 4)
         self.col_bond = None          # int32 (M,)
+        self.col_slot = None          # int32 (M,) compact Bond number inside each 256-column tile of a kind
+        self.max_slots = 0
+        self.tile_span = None         # int32 (T, 2): (first bead, beads) of the range each tile gathers from
+        self.max_span = 0
         self.bond_cols = []           # per bond: int64 column ids in instance order
         self.bond_indices = []        # per bond: int32 (n_inst, natoms) -- what mdtraj would receive
         self.natoms = None            # int32 (n_bonds,)
@@ -173,8 +177,13 @@ class _MeasureState:
         cols = self.plan.bond_cols[bond_id]
         if len(cols) == 0 or self.n_frames == 0:
             return np.zeros(0, dtype=np.float32)
-        idx = torch.from_numpy(cols).to(self.dev)
-        return self.values.index_select(1, idx).reshape(-1).cpu().numpy()
+        # values are stored as one (F, n_kind) plane per kind (see include/pycgtool_b200.h)
+        n2, n3, n4 = self.plan.counts
+        kind = int(self.plan.natoms[bond_id])
+        col0, n_k = {2: (0, n2), 3: (n2, n3), 4: (n2 + n3, n4)}[kind]
+        plane = self.values[self.n_frames * col0:self.n_frames * (col0 + n_k)].view(self.n_frames, n_k)
+        idx = torch.from_numpy(cols - col0).to(self.dev)
+        return plane.index_select(1, idx).reshape(-1).cpu().numpy()
 
     def invert(self, temp):
         """Cross-GPU reduction, dihedral pass 2 and the epilogue kernel (idempotent per ``temp``)."""
@@ -193,8 +202,9 @@ class _MeasureState:
                 dist.allreduce_sum(self.hist)
             if n4:
                 # dihedrals: the circular mean is final now, so finish <wrap(v - mean)^2> (util.py:49-53)
-                _lib.check(lib.cgb_circular_pass2(device.dptr(self.values), self.n_frames, n2 + n3 + n4,
-                                                  device.dptr(d["col_bond"]), n2 + n3, n4,
+                plane4 = self.values[self.n_frames * (n2 + n3):]
+                _lib.check(lib.cgb_circular_pass2(device.dptr(plane4), self.n_frames, n4,
+                                                  device.dptr(d["col_bond"][n2 + n3:]), n4,
                                                   device.dptr(self.partials), stream), "cgb_circular_pass2")
                 if dist.is_distributed():
                     wrapped = self.partials[:, 5].contiguous()
@@ -244,6 +254,7 @@ class BondSet:
         self._functional_forms = self._get_default_func_forms(options)
         self.histogram_bins = getattr(options, "histogram_bins", HIST_BINS)
         self.histogram_ranges = dict(HIST_RANGES)
+        self.staged = True            # stream bead tiles through shared memory (False: gather from global)
         self._plans = {}
         self._state = None
 
@@ -455,7 +466,51 @@ class BondSet:
         plan.counts = tuple(counts)
         plan.col_beads = (np.concatenate(col_beads, axis=0) if col_beads else np.zeros((0, 4))).astype(np.int32)
         plan.col_bond = (np.concatenate(col_bond) if col_bond else np.zeros(0)).astype(np.int32)
+        plan.col_slot, plan.max_slots = self._tile_slots(plan.col_bond, plan.counts)
+        plan.tile_span, plan.max_span = self._tile_spans(plan.col_beads, plan.counts)
         return plan
+
+    @staticmethod
+    def _tile_spans(col_beads, counts):
+        """Contiguous bead range covering each tile of ``CGB_MEASURE_TILE`` columns (staged kernels)."""
+        tile = _lib.MEASURE_TILE
+        rows, start = [], 0
+        for n_k in counts:
+            if n_k:
+                block = col_beads[start:start + n_k]
+                lo, hi = block.min(axis=1), block.max(axis=1)
+                cuts = np.arange(0, n_k, tile)
+                first = np.minimum.reduceat(lo, cuts)
+                last = np.maximum.reduceat(hi, cuts)
+                rows.append(np.stack([first, last - first + 1], axis=1))
+            start += n_k
+        if not rows:
+            return np.zeros((0, 2), dtype=np.int32), 0
+        spans = np.concatenate(rows, axis=0).astype(np.int32)
+        return spans, int(spans[:, 1].max())
+
+    @staticmethod
+    def _tile_slots(col_bond, counts):
+        """Number the distinct Bonds inside every tile of ``CGB_MEASURE_TILE`` consecutive columns of a
+        kind (see ``include/pycgtool_b200.h``): the measurement CTAs keep per-Bond sums and histograms
+        in shared memory indexed by this compact slot."""
+        tile = _lib.MEASURE_TILE
+        slots = np.zeros(len(col_bond), dtype=np.int32)
+        max_slots, start = 0, 0
+        for n_k in counts:
+            bonds = col_bond[start:start + n_k].astype(np.int64)
+            if n_k:
+                width = min(n_k, tile)
+                tile_id = np.arange(n_k) // width
+                # rank of each (tile, bond) pair among the pairs of its tile
+                key = tile_id * (int(bonds.max()) + 1) + bonds
+                uniq, inverse = np.unique(key, return_inverse=True)
+                first_of_tile = np.searchsorted(uniq // (int(bonds.max()) + 1), np.arange(tile_id[-1] + 1))
+                local = inverse - first_of_tile[tile_id]
+                slots[start:start + n_k] = local
+                max_slots = max(max_slots, int(local.max()) + 1)
+            start += n_k
+        return slots, max_slots
 
     def _plan_for(self, topology):
         key = id(topology)
@@ -479,6 +534,8 @@ class BondSet:
             plan._dev[key] = {
                 "col_beads": device.to_device(plan.col_beads, dev),
                 "col_bond": device.to_device(plan.col_bond, dev),
+                "col_slot": device.to_device(plan.col_slot, dev),
+                "tile_span": device.to_device(plan.tile_span, dev),
                 "natoms": device.to_device(plan.natoms, dev),
             }
         return plan._dev[key]
@@ -521,7 +578,7 @@ class BondSet:
         box_dev, ortho = traj.device_box_vectors(dev), int(traj.orthorhombic)
         mark("box")
 
-        values = torch.empty((n_frames, n_cols), dtype=torch.float32, device=dev)
+        values = torch.empty(n_frames * n_cols, dtype=torch.float32, device=dev)   # one plane per kind
         partials = torch.zeros((plan.n_bonds, _lib.NPART), dtype=torch.float64, device=dev)
         hist = hist_lo = hist_hi = lo = hi = None
         if histogram and plan.n_bonds:
@@ -538,7 +595,10 @@ class BondSet:
 
         def measure(nf, vals, parts, shift, hst):
             _lib.check(lib.cgb_measure(device.dptr(xyz), device.dptr(box_dev), ortho, nf, plan.n_beads,
-                                       device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), n2, n3, n4,
+                                       device.dptr(d["col_beads"]), device.dptr(d["col_bond"]),
+                                       device.dptr(d["col_slot"]), plan.max_slots,
+                                       device.dptr(d["tile_span"]) if self.staged else None, plan.max_span,
+                                       n2, n3, n4,
                                        plan.n_bonds, device.dptr(shift), device.dptr(vals), device.dptr(parts),
                                        device.dptr(hst), device.dptr(hist_lo), device.dptr(hist_hi),
                                        int(self.histogram_bins), stream), "cgb_measure")
@@ -554,7 +614,8 @@ class BondSet:
                 d["first_col"] = device.to_device(first_col, dev)
                 d["has_col"] = device.to_device(np.array([len(cols) > 0 for cols in plan.bond_cols]), dev)
             has = d["has_col"]
-            picked = values[0].index_select(0, d["first_col"])
+            # the one-frame pre-pass wrote planes of a 1-frame trajectory: plane offset 1*c0 == column index
+            picked = values[:n_cols].index_select(0, d["first_col"])
             shift = torch.where(has & torch.isfinite(picked), picked, torch.zeros_like(picked)).contiguous()
         dist.broadcast(shift, src=0)
         mark("shift")

@@ -192,23 +192,6 @@ struct MapParams {
     int32_t contiguous;   // tile == whole frame: one bulk copy per stage
 };
 
-__device__ __forceinline__ uint32_t head_floats(const float* p) {
-    return (uint32_t)((reinterpret_cast<uintptr_t>(p) & 15u) >> 2);
-}
-
-// Stage `nfl` floats starting at `src` into `slot` so that float i lands at slot[head + i].
-// Interior runs go through one bulk copy from the 16-byte-aligned address below `src`; a run that
-// would touch bytes outside [lo, hi) (only the first / last bytes of the whole array) is copied by
-// the producer warp with plain loads.  Returns the number of bytes the mbarrier must expect.
-__device__ __forceinline__ uint32_t span_bytes(const float* src, uint32_t nfl, uintptr_t lo, uintptr_t hi,
-                                               bool* edge) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    const uintptr_t a0 = a & ~uintptr_t(15);
-    const uintptr_t e1 = (a + 4u * (uintptr_t)nfl + 15u) & ~uintptr_t(15);
-    *edge = (a0 < lo) || (e1 > hi);
-    return *edge ? 0u : (uint32_t)(e1 - a0);
-}
-
 // Packed float32x2 arithmetic (sm_100 FADD2): two frames per instruction, each half rounded to
 // nearest exactly like the scalar operation.  The multiply stays scalar on purpose: ptxas contracts
 // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would change the reference's rounding.

@@ -16,7 +16,12 @@ from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth  # noqa: 
 from pycgtool_b200.synth import Options  # noqa: E402
 
 
+STAGED = "--gather" not in sys.argv
+
+
 def main():
+    if "--gather" in sys.argv:
+        sys.argv.remove("--gather")
     which = sys.argv[1] if len(sys.argv) > 1 else "s3"
     dev = torch.device("cuda")
     lib = _lib.load()
@@ -52,8 +57,9 @@ def main():
         h = torch.zeros_like(st.hist) if hist else None
         # column counts can only be switched off from the tail, so time cumulative prefixes
         _lib.check(lib.cgb_measure(device.dptr(cgx), device.dptr(box_dev), 1, frames, plan.n_beads,
-                                   device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), c2, c3, c4,
-                                   plan.n_bonds, device.dptr(st.shift), device.dptr(values) if vals else None,
+                                   device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), device.dptr(d["col_slot"]),
+                                   plan.max_slots, device.dptr(d["tile_span"]) if STAGED else None, plan.max_span,
+                                   c2, c3, c4, plan.n_bonds, device.dptr(st.shift), device.dptr(values) if vals else None,
                                    device.dptr(parts), device.dptr(h), device.dptr(torch.from_numpy(st.hist_lo).to(dev)),
                                    device.dptr(torch.from_numpy(st.hist_hi).to(dev)), 128, stream))
 
@@ -78,7 +84,8 @@ def main():
     timed("lengths only", n2, 0, 0)
     timed("lengths+angles", n2, n3, 0)
     m = frames * (n2 + n3 + n4)
-    nbytes = frames * (12 * plan.n_beads + 4 * (n2 + n3 + n4) + 36)
+    touched = len(np.unique(plan.col_beads))
+    nbytes = frames * (12 * touched + 4 * (n2 + n3 + n4) + 36)   # 12 B per bead touched
     print(f"measures {m:.3e}  {m / t_all / 1e-3:.3e} measures/s  algorithmic {nbytes / 1e9:.3f} GB -> "
           f"{nbytes / t_all / 1e6:.1f} GB/s")
 

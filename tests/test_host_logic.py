@@ -39,7 +39,7 @@ def test_abi_argument_errors_without_gpu():
     lib = _lib.load()
     assert lib.cgb_map_tiles(None, None, 4, 10, 2, None, 1, None, None, 8, 8, None, None) == -1
     assert lib.cgb_map_tiles(None, None, 0, 10, 2, None, 1, None, None, 8, 8, None, None) == 0   # no frames: no-op
-    assert lib.cgb_measure(None, None, 1, -1, 2, None, None, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == -1
+    assert lib.cgb_measure(None, None, 1, -1, 2, None, None, None, 0, None, 0, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == -1
     assert lib.cgb_boltzmann(None, None, None, None, 310.0, 3, None, None) == -1
     assert lib.cgb_map_set_tuning(-5, 0, 0) == -1
     with pytest.raises(RuntimeError):
@@ -181,6 +181,14 @@ def test_bond_assignment_bit_exact(golden, options, gro, bnd):
     n2, n3, n4 = plan.counts
     kinds = plan.natoms[plan.col_bond]
     assert (kinds[:n2] == 2).all() and (kinds[n2:n2 + n3] == 3).all() and (kinds[n2 + n3:] == 4).all()
+    # tile slots: inside every 256-column tile of a kind, slot <-> Bond is a bijection
+    start = 0
+    for n_k in plan.counts:
+        width = min(n_k, 256) if n_k else 1
+        for t0 in range(start, start + n_k, width):
+            sl, bd = plan.col_slot[t0:t0 + width], plan.col_bond[t0:t0 + width]
+            assert len(set(zip(sl, bd))) == len(set(sl)) == len(set(bd)) and sl.max() < plan.max_slots
+        start += n_k
 
 
 def test_generated_angles_and_s5_term_count(options):

@@ -59,7 +59,7 @@ def write_gro(path, traj, frame=0):
     topologies built in memory, 3 decimals, always nine box fields)."""
     top = traj.topology
     xyz = traj.xyz[frame]
-    lines = ["Generated with MDTraj, t= %s" % float(traj.time[frame]), "%5d" % top.n_atoms]
+    lines = ["Generated with MDTraj, t= %s" % float(traj.time[frame]), " %d" % top.n_atoms]
     res_of_atom = np.repeat(np.arange(top.n_residues), np.diff(top.res_first))
     for i in range(top.n_atoms):
         r = int(res_of_atom[i])

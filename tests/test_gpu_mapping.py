@@ -69,6 +69,24 @@ def test_reference_kats(golden, options):
     np.testing.assert_allclose(cg.residue(0).atom(0).coords, [[1.5, 1.5, 1.5]])
 
 
+def test_saved_gro_is_byte_identical_to_reference_output(golden, options, tmp_path):
+    # reference tests/test_mapping.py:89-101: water.gro + water.map -> water-cg.gro, compared with filecmp
+    import filecmp
+    _, _, cg = _product_map(golden, "water.gro", "water.map", options)
+    out = tmp_path / "water-cg.gro"
+    cg.save(out)
+    assert filecmp.cmp(golden / "water-cg.gro", out, shallow=False)
+    # reference tests/test_pycgtool.py:112-118: first frame of the mapped sugar vs sugar_out.gro (rtol 1e-3)
+    from pycgtool_b200 import formats
+    _, _, cg = _product_map(golden, "sugar.gro", "sugar.map", options, xtc="sugar.xtc")
+    out = tmp_path / "out.gro"
+    cg.save(out, frame_number=0)
+    mine, ref = formats.read_gro(out), formats.read_gro(golden / "sugar_out.gro")
+    assert mine.topology == ref.topology
+    np.testing.assert_allclose(mine.xyz, ref.xyz, rtol=1e-3)
+    np.testing.assert_allclose(mine.unitcell_vectors, ref.unitcell_vectors, rtol=1e-3)
+
+
 def test_empty_result_frame(golden, options):
     # reference tests/test_mapping.py:247-258
     _, _, cg = _product_map(golden, "sugar.gro", "water.map", options)
@@ -181,6 +199,29 @@ def test_unaligned_frame_slices(options):
         for f0, f1 in ((0, n_frames), (5, 18), (22, 23)):
             out = mapper.map_device(plan, view[f0:f1], lengths[f0:f1])
             assert np.array_equal(out.cpu().numpy(), ref[f0:f1]), (shift, f0, f1)
+
+
+def test_output_canaries_untouched(options):
+    """compute-sanitizer is closed on the GPU pool, so out-of-bounds *writes* are checked by hand: the
+    output lives inside a larger buffer of sentinels which must survive, for several shapes."""
+    import torch
+    from pycgtool_b200 import Mapping, synth
+    dev = torch.device("cuda")
+    for sysm, n_frames in ((synth.membrane(3, 11, seed=5), 13), (synth.small_molecule(), 301)):
+        xyz = torch.from_numpy(sysm.coordinates_host(n_frames)).to(dev)
+        box = sysm.box_vectors(n_frames)
+        lengths = np.stack([box[:, 0, 0], box[:, 1, 1], box[:, 2, 2]], axis=1)
+        map_path, _ = sysm.write_files()
+        mapper = Mapping(map_path, options)
+        plan = mapper.compile_plan(sysm.topology)
+        n_out = n_frames * plan.n_beads * 3
+        guard = 257
+        buf = torch.full((n_out + 2 * guard,), -12345.0, dtype=torch.float32, device=dev)
+        out = buf[guard:guard + n_out].view(n_frames, plan.n_beads, 3)
+        mapper.map_device(plan, xyz, lengths, out=out)
+        torch.cuda.synchronize()
+        assert (buf[:guard] == -12345.0).all() and (buf[guard + n_out:] == -12345.0).all()
+        assert not (out == -12345.0).any()
 
 
 @pytest.mark.parametrize("stage_bytes,n_stages,fpc,threads,fg", [

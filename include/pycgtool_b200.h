@@ -189,6 +189,46 @@ enum {
 int cgb_boltzmann(const double* partials, const float* shift, const int32_t* natoms, const int32_t* form,
                   double temperature, int64_t n_bonds, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Trajectory ingest: GROMACS .xtc (the caller of the hot path, reference pycgtool/frame.py:41-63, where the
+ * reference calls mdtraj's C codec).  The file image is scanned on the host, the compressed coordinate
+ * payloads are decoded on the GPU (one thread per frame) straight into the [F][N][3] float32 trajectory.
+ * Coordinates are float32(int) * float32(1 / precision), the xdrfile convention.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct CgbXtcFrame {     /* 48 bytes */
+    int64_t offset;              /* byte offset of the coordinate payload inside the file image */
+    int32_t nbytes;              /* payload bytes (12 * natoms raw big-endian floats when natoms <= 9) */
+    int32_t natoms;
+    int32_t minint[3];
+    int32_t maxint[3];
+    int32_t smallidx;
+    float precision;
+} CgbXtcFrame;
+
+/* Host: walk the frame headers of a file image.  frames == NULL only counts.  box: float32 [F][9] row
+ * vectors, time: float32 [F], step: int32 [F] (each may be NULL).  CGB_EINVAL on a malformed image or a
+ * changing atom count, CGB_ERANGE when max_frames is too small. */
+int cgb_xtc_scan(const uint8_t* data, int64_t n_bytes, int64_t max_frames, CgbXtcFrame* frames,
+                 float* box, float* time, int32_t* step, int64_t* n_frames, int32_t* n_atoms);
+
+/* GPU: decode `n_frames` (<= 65535 per call) frames of the file image `data` (device memory, 4-byte aligned,
+ * n_bytes long and readable up to 8 bytes past the end) into xyz (device float32 [n_frames][n_atoms][3]).
+ * frames: device copy of the table from cgb_xtc_scan (its offsets are relative to `data`).  Two kernels: a
+ * sequential walk per frame that records a checkpoint every 16 coordinate groups, then one thread per
+ * checkpoint decodes in parallel.  workspace: device scratch of cgb_xtc_workspace_bytes(), 16-byte aligned. */
+int64_t cgb_xtc_workspace_bytes(int64_t n_frames, int64_t n_atoms);
+int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtcFrame* frames, int64_t n_frames,
+                   int64_t n_atoms, float* xyz, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Host: the same decoder on the CPU (all pointers host memory). */
+int cgb_xtc_decode_host(const uint8_t* data, const CgbXtcFrame* frames, int64_t n_frames, int64_t n_atoms,
+                        float* xyz);
+
+/* Host: encode frames as .xtc into out[capacity]; *n_written receives the size of the image.  Returns
+ * CGB_ERANGE (with *n_written set) when capacity is too small.  box: [F][9] or NULL, time: [F] or NULL. */
+int cgb_xtc_encode(const float* xyz, const float* box, const float* time, int64_t n_frames, int64_t n_atoms,
+                   float precision, uint8_t* out, int64_t capacity, int64_t* n_written);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,9 @@ FORM_IDS = {
 FORM_STATS_ONLY = 5
 
 
+XTC_FRAME_BYTES = 48  # sizeof(CgbXtcFrame)
+
+
 class MapTile(ctypes.Structure):
     _fields_ = [
         ("atom0", ctypes.c_int32),
@@ -55,6 +58,11 @@ SIGNATURES = {
     "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "cgb_value_stats": (_int, [_vp, _i64, _int, ctypes.c_float, _vp, _vp]),
     "cgb_boltzmann": (_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _i64, _vp, _vp]),
+    "cgb_xtc_scan": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cgb_xtc_workspace_bytes": (_i64, [_i64, _i64]),
+    "cgb_xtc_decode": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "cgb_xtc_decode_host": (_int, [_vp, _vp, _i64, _i64, _vp]),
+    "cgb_xtc_encode": (_int, [_vp, _vp, _vp, _i64, _i64, ctypes.c_float, _vp, _i64, _vp]),
 }
 
 _lib = None

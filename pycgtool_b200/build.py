@@ -13,7 +13,7 @@ import shutil
 import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
-SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_boltzmann.cu"]
+SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_boltzmann.cu", "cgb_xtc.cu"]
 HEADERS = [CSRC / "cgb_common.cuh", CSRC.parent.parent / "include" / "pycgtool_b200.h"]
 LIBRARY = CSRC / "libpycgtool_b200.so"
 STAMP = CSRC / ".build_stamp"

@@ -1,16 +1,20 @@
-"""Minimal GRO / XTC readers and a GRO writer.
+"""GRO / XTC file formats.
 
 The reference delegates file I/O to mdtraj (``pycgtool/frame.py:41-63,231-244``),
 which is not available here; this module covers what the hot path's callers
-need to run the reference's own fixtures: GROMACS ``.gro`` (read / write, with
-mdtraj's water renaming) and ``.xtc`` (read).  I/O is host-side Python and is
-not part of the accelerated path.
+need: GROMACS ``.gro`` (read / write, with mdtraj's water renaming) and ``.xtc``
+(read / write).  The XTC codec lives in the shared library (``csrc/cgb_xtc.cu``):
+``read_xtc`` decodes on the host through it, ``read_xtc_device`` uploads the
+*compressed* file image and decodes on the GPU, one thread per frame, straight
+into the device-resident trajectory the mapping kernel reads.
 """
 
+import ctypes
 import struct
 
 import numpy as np
 
+from . import _lib
 from .topology import Topology, Trajectory
 
 # mdtraj renames residues / atoms through its PDB tables when it builds a
@@ -74,123 +78,114 @@ def write_gro(path, traj, frame=0):
 
 
 # ------------------------------------------------------------------------------- XTC
-_FIRST = 9
-_MAGIC = (0,) * 9 + (
-    8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512, 645, 812,
-    1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007,
-    32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127,
-    524287, 660561, 832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304,
-    5284491, 6658042, 8388607, 10568983, 13316085, 16777216)
+def _scan_xtc(image):
+    """Frame table, boxes and times of an XTC file image (numpy uint8) through ``cgb_xtc_scan``."""
+    lib = _lib.load()
+    n_frames, n_atoms = ctypes.c_int64(), ctypes.c_int32()
+    _lib.check(lib.cgb_xtc_scan(_lib.ptr(image), image.size, 0, None, None, None, None,
+                                ctypes.byref(n_frames), ctypes.byref(n_atoms)), "cgb_xtc_scan")
+    nf = n_frames.value
+    table = np.zeros(nf * _lib.XTC_FRAME_BYTES, dtype=np.uint8)
+    box = np.zeros((nf, 3, 3), dtype=np.float32)
+    time = np.zeros(nf, dtype=np.float32)
+    _lib.check(lib.cgb_xtc_scan(_lib.ptr(image), image.size, nf, _lib.ptr(table), _lib.ptr(box), _lib.ptr(time),
+                                None, ctypes.byref(n_frames), ctypes.byref(n_atoms)), "cgb_xtc_scan")
+    return table, box, time, nf, n_atoms.value
 
 
-def _unpack_frame(natoms, lo, hi, smallidx, payload):
-    """xdrfile ``xdr3dfcoord`` integer decoder for one frame -> (natoms, 3) int32."""
-    size = [hi[d] - lo[d] + 1 for d in range(3)]
-    wide = any(s > 0xFFFFFF for s in size)
-    nbits_each = [s.bit_length() for s in size]
-    nbits_all = (size[0] * size[1] * size[2]).bit_length()
-    stream = int.from_bytes(payload, "big")
-    remaining = 8 * len(payload)
-
-    def bits(n):
-        nonlocal remaining
-        remaining -= n
-        return (stream >> remaining) & ((1 << n) - 1)
-
-    def triple(n, radix):
-        # bytes arrive least-significant first; the last chunk may be partial
-        acc, shift = 0, 0
-        while n > 8:
-            acc |= bits(8) << shift
-            shift += 8
-            n -= 8
-        if n:
-            acc |= bits(n) << shift
-        acc, z = divmod(acc, radix[2])
-        x, y = divmod(acc, radix[1])
-        return x, y, z
-
-    half = _MAGIC[smallidx] // 2
-    below = _MAGIC[max(_FIRST, smallidx - 1)] // 2
-    out = np.empty((natoms + 8, 3), dtype=np.int64)
-    n, run = 0, 0
-    while n < natoms:
-        if wide:
-            cur = [bits(nbits_each[d]) + lo[d] for d in range(3)]
-        else:
-            t = triple(nbits_all, size)
-            cur = [t[d] + lo[d] for d in range(3)]
-        change = 0
-        if bits(1):
-            run = bits(5)
-            change = run % 3
-            run -= change
-            change -= 1
-        if run > 0:
-            small_radix = (_MAGIC[smallidx],) * 3
-            anchor = cur
-            for k in range(0, run, 3):
-                t = triple(smallidx, small_radix)
-                nxt = [t[d] + anchor[d] - half for d in range(3)]
-                if k == 0:
-                    out[n] = nxt        # water trick: the second atom is stored first
-                    out[n + 1] = anchor
-                    n += 2
-                else:
-                    out[n] = nxt
-                    n += 1
-                anchor = nxt
-        else:
-            out[n] = cur
-            n += 1
-        smallidx += change
-        if change < 0:
-            half = below
-            below = _MAGIC[smallidx - 1] // 2 if smallidx > _FIRST else 0
-        elif change > 0:
-            below = half
-            half = _MAGIC[smallidx] // 2
-    return out[:natoms].astype(np.int32)
+def _check_topology(topology, n_atoms):
+    if topology is not None and topology.n_atoms != n_atoms:
+        raise ValueError("Number of atoms does not match between topology and trajectory files")
 
 
 def read_xtc(path, topology=None):
-    """.xtc -> ``Trajectory``.  Coordinates are ``float32(int) * float32(1/precision)``."""
-    with open(path, "rb") as handle:
-        blob = handle.read()
-    pos, frames, times, boxes = 0, [], [], []
-    while pos < len(blob):
-        magic, natoms, _step, time = struct.unpack_from(">iiif", blob, pos)
-        if magic != 1995:
-            raise OSError("XTC magic number mismatch: format is not supported")
-        boxes.append(np.frombuffer(blob, ">f4", 9, pos + 16).astype(np.float32).reshape(3, 3))
-        (count,) = struct.unpack_from(">i", blob, pos + 52)
-        pos += 56
-        if count <= 9:
-            coords = np.frombuffer(blob, ">f4", 3 * count, pos).astype(np.float32)
-            pos += 12 * count
-        else:
-            precision, = struct.unpack_from(">f", blob, pos)
-            lo = struct.unpack_from(">3i", blob, pos + 4)
-            hi = struct.unpack_from(">3i", blob, pos + 16)
-            smallidx, nbytes = struct.unpack_from(">2i", blob, pos + 28)
-            pos += 36
-            ints = _unpack_frame(count, lo, hi, smallidx, blob[pos:pos + nbytes])
-            pos += -(-nbytes // 4) * 4
-            coords = ints.astype(np.float32).reshape(-1) * (np.float32(1.0) / np.float32(precision))
-        frames.append(coords.reshape(count, 3))
-        times.append(time)
-    xyz = np.stack(frames).astype(np.float32)
-    if topology is not None and topology.n_atoms != xyz.shape[1]:
-        raise ValueError("Number of atoms does not match between topology and trajectory files")
-    box = np.stack(boxes)
-    return Trajectory(xyz, topology, np.array(times, dtype=np.float32), box if box.any() else None)
+    """.xtc -> ``Trajectory`` decoded on the host (C codec in the shared library).
+    Coordinates are ``float32(int) * float32(1/precision)``."""
+    image = np.fromfile(path, dtype=np.uint8)
+    try:
+        table, box, time, nf, n_atoms = _scan_xtc(image)
+    except RuntimeError as exc:
+        raise OSError(f"'{path}': XTC format is not supported ({exc})") from exc
+    _check_topology(topology, n_atoms)
+    xyz = np.empty((nf, n_atoms, 3), dtype=np.float32)
+    padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
+    _lib.check(_lib.load().cgb_xtc_decode_host(_lib.ptr(padded), _lib.ptr(table), nf, n_atoms, _lib.ptr(xyz)),
+               "cgb_xtc_decode_host")
+    return Trajectory(xyz, topology, time, box if box.any() else None)
 
 
-def load(path, top=None):
-    """Dispatch on extension, like ``mdtraj.load`` for the supported formats."""
+def read_xtc_device(path, topology=None, device=None):
+    """.xtc -> ``Trajectory`` whose coordinates are decoded on the GPU and stay there.
+
+    Only the compressed file image crosses PCIe; ``cgb_xtc_decode`` expands it in HBM."""
+    import torch
+    from . import device as dev
+    device = device or dev.default_device()
+    image = np.fromfile(path, dtype=np.uint8)
+    try:
+        table, box, time, nf, n_atoms = _scan_xtc(image)
+    except RuntimeError as exc:
+        raise OSError(f"'{path}': XTC format is not supported ({exc})") from exc
+    _check_topology(topology, n_atoms)
+    padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
+    image_dev = dev.to_device(padded, device)
+    table_dev = dev.to_device(table, device)
+    xyz = torch.empty((nf, n_atoms, 3), dtype=torch.float32, device=device)
+    decode_device(image_dev, image.size, table_dev, nf, n_atoms, xyz)
+    torch.cuda.current_stream().synchronize()      # image_dev / table_dev may be released now
+    return Trajectory(None, topology, time, box if box.any() else None, xyz_device=xyz)
+
+
+def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, block=4096):
+    """``cgb_xtc_decode`` over blocks of frames (one launch handles at most 65535 frames; the
+    checkpoint workspace is sized for one block and reused)."""
+    import torch
+    from . import device as dev
+    lib = _lib.load()
+    block = int(min(block, max(n_frames, 1)))
+    ws_bytes = int(lib.cgb_xtc_workspace_bytes(block, n_atoms))
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz_dev.device)
+    frame_bytes = _lib.XTC_FRAME_BYTES
+    for f0 in range(0, n_frames, block):
+        f1 = min(n_frames, f0 + block)
+        _lib.check(lib.cgb_xtc_decode(dev.dptr(image_dev), n_bytes, dev.dptr(table_dev[f0 * frame_bytes:]),
+                                      f1 - f0, n_atoms, dev.dptr(xyz_dev[f0:]), dev.dptr(workspace), ws_bytes,
+                                      dev.stream_handle()), "cgb_xtc_decode")
+
+
+def encode_xtc(xyz, unitcell_vectors=None, time=None, precision=1000.0):
+    """(F, N, 3) float32 coordinates -> XTC file image (numpy uint8), via ``cgb_xtc_encode``."""
+    lib = _lib.load()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    nf, n_atoms = xyz.shape[0], xyz.shape[1]
+    box = None if unitcell_vectors is None else np.ascontiguousarray(unitcell_vectors, dtype=np.float32).reshape(nf, 9)
+    tm = None if time is None else np.ascontiguousarray(time, dtype=np.float32)
+    capacity = 4096 + nf * (128 + 8 * n_atoms)
+    written = ctypes.c_int64()
+    for _ in range(2):
+        out = np.empty(capacity, dtype=np.uint8)
+        rc = lib.cgb_xtc_encode(_lib.ptr(xyz), _lib.ptr(box), _lib.ptr(tm), nf, n_atoms, float(precision),
+                                _lib.ptr(out), capacity, ctypes.byref(written))
+        if rc == 0:
+            return out[:written.value].copy()
+        if rc != -2 or written.value <= capacity:
+            _lib.check(rc, "cgb_xtc_encode")
+        capacity = written.value
+    raise RuntimeError("cgb_xtc_encode: buffer negotiation failed")
+
+
+def write_xtc(path, traj, precision=1000.0):
+    """Write every frame of ``traj`` as .xtc."""
+    image = encode_xtc(traj.xyz, traj.unitcell_vectors, traj.time, precision)
+    image.tofile(path)
+
+
+def load(path, top=None, on_device=False):
+    """Dispatch on extension, like ``mdtraj.load`` for the supported formats.  ``on_device`` decodes
+    an .xtc on the GPU (``read_xtc_device``)."""
     suffix = str(path).lower().rsplit(".", 1)[-1]
     if suffix == "gro":
         return read_gro(path)
     if suffix == "xtc":
-        return read_xtc(path, top)
+        return read_xtc_device(path, top) if on_device else read_xtc(path, top)
     raise OSError(f"'{path}': format is not supported")

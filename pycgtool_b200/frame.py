@@ -37,7 +37,10 @@ class NonMatchingSystemError(ValueError):
 class Frame:
     """Topology plus trajectory, loaded fully into memory (``frame.py:69-117``)."""
 
-    def __init__(self, topology_file=None, trajectory_file=None, frame_start=0, frame_end=None):
+    def __init__(self, topology_file=None, trajectory_file=None, frame_start=0, frame_end=None,
+                 device_decode=False):
+        """``device_decode=True`` expands an .xtc trajectory on the GPU (only the compressed file
+        crosses PCIe) and leaves the coordinates device-resident for ``Mapping.apply``."""
         if topology_file is None:
             self._topology = Topology()   # an empty frame to be filled in (CG output)
             self._topology._owner = self
@@ -47,7 +50,8 @@ class Frame:
             self._topology = traj.topology
             if trajectory_file is not None:
                 try:
-                    traj = formats.load(trajectory_file, top=self._topology)
+                    traj = formats.load(trajectory_file, top=self._topology,
+                                        on_device=device_decode and frame_start == 0)
                 except ValueError as exc:
                     raise NonMatchingSystemError from exc
                 # frame.py:119-136: frame_end only applies together with a non-zero frame_start
@@ -128,11 +132,14 @@ class Frame:
 
     # ------------------------------------------------------------------ output
     def save(self, filename, frame_number=None, **kwargs):
-        """Write the trajectory (.gro: one frame)."""
+        """Write the trajectory (.gro: one frame; .xtc: all frames or the selected one)."""
         from . import util
         filename = pathlib.Path(filename)
         util.backup_file(filename)
         if filename.suffix.lower() == ".gro":
             formats.write_gro(filename, self._trajectory, 0 if frame_number is None else frame_number)
+        elif filename.suffix.lower() == ".xtc":
+            traj = self._trajectory if frame_number is None else self._trajectory.slice(frame_number)
+            formats.write_xtc(filename, traj, **kwargs)
         else:
             raise UnsupportedFormatException(f"cannot write '{filename.suffix}' files")

@@ -32,7 +32,7 @@ COPIES = [
     "martini3/four.gro", "martini3/four.map", "martini3/four.itp",
     "martini3/naphthalene.gro", "martini3/naphthalene.map", "martini3/naphthalene.bnd",
     "martini3/naphthalene_out.itp",
-    "ffout.ff/out.rtp",
+    "ffout.ff/out.rtp", "ffout.ff/out.r2b",
 ]
 
 

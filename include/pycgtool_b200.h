@@ -156,6 +156,10 @@ int cgb_measure(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_
                 unsigned long long* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
                 void* stream);
 
+/* Benchmarking knobs of the staged K2 kernels: bytes per pipeline stage (1 KiB .. 48 KiB) and pipeline
+ * depth (2 .. 4).  Not needed for correctness. */
+int cgb_measure_set_tuning(int32_t stage_bytes, int32_t n_stages);
+
 /* Pass 2 for dihedral columns: partials[b][5] += sum over the bond's values of wrap(v - m_b)^2 with
  * m_b = atan2(partials[b][4], partials[b][3]) (util.py:40-53).  Call after partials[.][3..4] are final
  * (i.e. after the cross-GPU reduction).  values: device pointer to the first of n_cols columns of a

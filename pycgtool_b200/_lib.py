@@ -53,6 +53,7 @@ SIGNATURES = {
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "cgb_map_set_tuning": (_int, [_i32, _i32, _i32]),
     "cgb_map_set_shape": (_int, [_i32, _i32]),
+    "cgb_measure_set_tuning": (_int, [_i32, _i32]),
     "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64,
                            _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),

@@ -22,9 +22,16 @@ STAGED = "--gather" not in sys.argv
 def main():
     if "--gather" in sys.argv:
         sys.argv.remove("--gather")
+    tune = [a for a in sys.argv if a.startswith("--tune=")]
+    for a in tune:
+        sys.argv.remove(a)
     which = sys.argv[1] if len(sys.argv) > 1 else "s3"
     dev = torch.device("cuda")
     lib = _lib.load()
+    if tune:
+        sb, ns = (int(x) for x in tune[0][7:].split(","))
+        _lib.check(lib.cgb_measure_set_tuning(sb, ns), "cgb_measure_set_tuning")
+        print(f"tuning: stage_bytes={sb} stages={ns}")
     if which == "s3":
         sysm, frames = synth.small_molecule(), int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
     else:
@@ -52,6 +59,8 @@ def main():
     values = st.values
     stream = device.stream_handle()
 
+    hist_lo, hist_hi = torch.from_numpy(st.hist_lo).to(dev), torch.from_numpy(st.hist_hi).to(dev)
+
     def run(c2, c3, c4, hist=True, vals=True):
         parts = torch.zeros_like(st.partials)
         h = torch.zeros_like(st.hist) if hist else None
@@ -60,8 +69,7 @@ def main():
                                    device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), device.dptr(d["col_slot"]),
                                    plan.max_slots, device.dptr(d["tile_span"]) if STAGED else None, plan.max_span,
                                    c2, c3, c4, plan.n_bonds, device.dptr(st.shift), device.dptr(values) if vals else None,
-                                   device.dptr(parts), device.dptr(h), device.dptr(torch.from_numpy(st.hist_lo).to(dev)),
-                                   device.dptr(torch.from_numpy(st.hist_hi).to(dev)), 128, stream))
+                                   device.dptr(parts), device.dptr(h), device.dptr(hist_lo), device.dptr(hist_hi), 128, stream))
 
     def timed(label, *args, **kw):
         for _ in range(2):

@@ -35,6 +35,8 @@ def main():
     stall = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     agg = {h: 0 for h in stall}
     for r in rows[2:]:
+        if len(r) < len(hdr) or not r[ci["# Samples"]].isdigit():
+            continue
         n, s = int(r[ci["Instructions Executed"]]), int(r[ci["# Samples"]])
         data.append((n, s, r))
         tot += n

@@ -134,7 +134,7 @@ int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
  *   [6] count of all values           [7] reserved
  * shift: device float32 [n_bonds] or NULL (0) -- any value near the data, identical on all shards.
  * hist: device uint64 [n_bonds][n_bins] accumulated, or NULL; bin edges are
- * linspace(hist_lo[b], hist_hi[b], n_bins + 1) with numpy.histogram's edge rules.
+ * linspace(hist_lo[b], hist_hi[b], n_bins + 1) with numpy.histogram's edge rules (1 <= n_bins <= 512).
  * ---------------------------------------------------------------------------------------------- */
 #define CGB_NPART 8
 /* col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one

@@ -92,6 +92,52 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 // Streaming (no L1 allocate) scalar store for write-once outputs.
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 
+// Packed float32x2 arithmetic (sm_100 FADD2): two frames per instruction, each half rounded to
+// nearest exactly like the scalar operation.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// (one rounding instead of two): mul2 below is the contraction-proof product, mulc2 the plain one.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// Packed product rounded to nearest, written as fma(a, b, +0) so that ptxas has no multiply to
+// contract with the add that follows (it folds mul.rn.f32x2 -- and even fma(a, b, -0) -- plus
+// add.rn.f32x2 into one FFMA2, which changes the rounding).  fma(a, b, +0) equals rn(a * b) except
+// that a product of -0 becomes +0; the accumulator it is added to starts at +0 and can never be -0,
+// so acc + (+0) == acc + (-0) and the sum is bit-identical to the reference's.
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    const uint64_t poszero2 = 0x0000000000000000ull;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(poszero2));
+    return r;
+}
+
+// Plain packed product; ptxas may contract it with a following add2 into one FFMA2.
+__device__ __forceinline__ uint64_t mulc2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t splat2(float a) { return pack2(a, a); }
+
 // ---------------------------------------------------------------- minimum image, one component
 // Exactly the reference expression v -= L * rint(v / L) (mapping.py:457) with IEEE divide,
 // round-half-even and un-fused multiply/subtract.  |v| <= 0.49 L  =>  rint(v / L) == 0 and the

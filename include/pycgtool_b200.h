@@ -14,7 +14,8 @@
  *   - plain pointers and sizes only; no C++ or torch types cross the boundary;
  *   - "device" pointers are CUDA device memory owned by the caller; "host" pointers are ordinary memory;
  *   - every launch is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream)
- *     and returns without synchronising; the library keeps no global state and allocates nothing;
+ *     and returns without synchronising; the library allocates nothing and keeps no state besides the
+ *     process-wide benchmarking knobs (cgb_map_set_tuning / cgb_map_set_shape / cgb_measure_set_tuning);
  *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative CGB_E* on bad arguments;
  *   - all index tables are int32; frames, atoms and beads are counted in int64.
  */

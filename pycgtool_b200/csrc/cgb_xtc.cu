@@ -271,7 +271,7 @@ __host__ __device__ inline void decode_raw(const uint8_t* payload, int natoms, f
 }
 
 // GPU decode in two kernels.  The bit stream of a frame is sequential, but finding where each group
-// starts only needs its flag / run bits: `xtc_walk_kernel` (one thread per frame) skips over the
+// starts only needs its flag / run bits: `xtc_walk_kernel` (one warp per frame) skips over the
 // coordinate fields and drops a checkpoint (bit position, atom index, table entry, run length) every
 // kCheckEvery groups; `xtc_decode_kernel` then decodes every checkpoint's groups with one thread each,
 // which is where the divisions, conversions and stores are.
@@ -293,51 +293,101 @@ __device__ __forceinline__ uint32_t peek_bits(const uint32_t* __restrict__ words
     return __funnelshift_l(lo, hi, sh) >> (32 - n);
 }
 
-__global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict__ data,
+// One warp per frame.  The 32 lanes stage the bit stream into a two-half ring in shared memory
+// (coalesced loads, bytes swapped to big-endian words once); lane 0 walks it.  A group's position
+// depends on the previous group's (flag, run) bits, so the walk is a dependent chain (real
+// trajectories set the flag in 40-100 % of the groups, so wider speculation across lanes does not pay;
+// measured).  The chain is kept short by peeking the *next* group at the position it has when the
+// current flag bit is 0 (run length and table entry unchanged), which takes the shared-memory load
+// out of the chain for those groups.  Throughput comes from walking all frames of a block at once.
+constexpr int kWalkHalfWords = 1024;                        // 4 KB per half of the ring
+constexpr uint32_t kWalkMarginBits = 2 * 96 + 8 * 72 + 64;  // two full coordinates, one run of smalls, slack
+
+__device__ __forceinline__ uint32_t ring_peek6(const uint32_t* ring, uint32_t pos) {
+    const uint32_t w = pos >> 5, sh = pos & 31;
+    const uint32_t hi = ring[w & (2 * kWalkHalfWords - 1)];
+    const uint32_t lo = ring[(w + 1) & (2 * kWalkHalfWords - 1)];
+    return __funnelshift_l(lo, hi, sh) >> 26;
+}
+
+__global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict__ data, int64_t n_bytes,
                                                       const CgbXtcFrame* __restrict__ frames, int64_t n_frames,
                                                       int64_t n_atoms, XtcCheckpoint* __restrict__ checks,
                                                       int32_t* __restrict__ n_checks) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_frames) return;
+    __shared__ uint32_t ring[2 * kWalkHalfWords];
+    const int64_t f = blockIdx.x;
+    const int lane = threadIdx.x;
     const CgbXtcFrame fr = frames[f];
     XtcCheckpoint* out = checks + f * checks_per_frame(n_atoms);
     if (fr.natoms <= 9) {
-        n_checks[f] = 0;
+        if (lane == 0) n_checks[f] = 0;
         return;
     }
     const FrameCoding c = frame_coding(fr);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(data + fr.offset);
-    // The only data dependence between groups is (flag, run): one 6-bit peek per group.
+    // words of the image readable from the payload start (the image is padded by 8 bytes)
+    const int64_t avail = (n_bytes + 8 - fr.offset) >> 2;
+
+    auto load_half = [&](int h) {
+        uint32_t* dst = ring + (h & 1) * kWalkHalfWords;
+        const int64_t w0 = (int64_t)h * kWalkHalfWords;
+#pragma unroll 8
+        for (int i = lane; i < kWalkHalfWords; i += 32) {
+            const int64_t w = w0 + i;
+            dst[i] = w < avail ? __byte_perm(__ldg(words + w), 0, 0x0123) : 0u;
+        }
+    };
+    load_half(0);
+    load_half(1);
+    __syncwarp();
+    int hl = 1;  // last half loaded; the ring holds halves hl - 1 and hl
+
     uint32_t pos = 0;
     int smallidx = fr.smallidx, run = 0, atom = 0, group = 0, nc = 0;
     const uint32_t fullbits = (uint32_t)c.fullbits;
-    while (atom < fr.natoms) {
-        if ((group & (kCheckEvery - 1)) == 0) {
-            XtcCheckpoint cp;
-            cp.bitpos = pos;
-            cp.atom = (uint32_t)atom;
-            cp.state = (uint32_t)smallidx | ((uint32_t)run << 8);
-            out[nc++] = cp;
+    for (;;) {
+        bool done = false;
+        if (lane == 0) {
+            const uint32_t limit_bits = (uint32_t)(hl + 1) * kWalkHalfWords * 32u;
+            uint32_t v = ring_peek6(ring, pos + fullbits);
+            while (atom < fr.natoms && pos + kWalkMarginBits < limit_bits) {
+                if ((group & (kCheckEvery - 1)) == 0) {
+                    XtcCheckpoint cp;
+                    cp.bitpos = pos;
+                    cp.atom = (uint32_t)atom;
+                    cp.state = (uint32_t)smallidx | ((uint32_t)run << 8);
+                    out[nc++] = cp;
+                }
+                // next group if this one's flag bit is 0: same run, same table entry
+                const uint32_t pos0 = pos + fullbits + 1u + (uint32_t)(run / 3) * (uint32_t)smallidx;
+                const uint32_t v0 = ring_peek6(ring, pos0 + fullbits);
+                if (v & 32u) {
+                    run = (int)(v & 31u);
+                    const int is_smaller = run % 3;
+                    run -= is_smaller;
+                    const int smalls = run / 3;
+                    pos += fullbits + 6u + (uint32_t)smalls * (uint32_t)smallidx;
+                    atom += smalls + 1;
+                    smallidx += is_smaller - 1;
+                    v = ring_peek6(ring, pos + fullbits);
+                } else {
+                    atom += run / 3 + 1;
+                    pos = pos0;
+                    v = v0;
+                }
+                ++group;
+            }
+            done = atom >= fr.natoms;
         }
-        pos += fullbits;
-        const uint32_t v = peek_bits(words, pos, 6);  // flag bit, then (if set) the 5-bit run field
-        int is_smaller = 0;
-        if (v & 32u) {
-            run = (int)(v & 31u);
-            is_smaller = run % 3;
-            run -= is_smaller;
-            is_smaller -= 1;
-            pos += 6;
-        } else {
-            pos += 1;
-        }
-        const int smalls = run / 3;
-        pos += (uint32_t)smalls * (uint32_t)smallidx;
-        atom += smalls + 1;
-        smallidx += is_smaller;
-        ++group;
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) break;
+        // pos lies in half hl by now (the margin is far smaller than a half): overwrite the older half
+        ++hl;
+        __syncwarp();
+        load_half(hl);
+        __syncwarp();
     }
-    n_checks[f] = nc;
+    if (lane == 0) n_checks[f] = nc;
 }
 
 __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restrict__ data,
@@ -552,7 +602,7 @@ extern "C" int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtc
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     XtcCheckpoint* checks = static_cast<XtcCheckpoint*>(workspace);
     int32_t* n_checks = reinterpret_cast<int32_t*>(checks + n_frames * checks_per_frame(n_atoms));
-    xtc_walk_kernel<<<(unsigned)((n_frames + 31) / 32), 32, 0, st>>>(data, frames, n_frames, n_atoms, checks,
+    xtc_walk_kernel<<<(unsigned)n_frames, 32, 0, st>>>(data, n_bytes, frames, n_frames, n_atoms, checks,
                                                                     n_checks);
     CGB_CUDA_TRY(cudaGetLastError());
     const int64_t max_checks = checks_per_frame(n_atoms);

@@ -114,43 +114,138 @@ def read_xtc(path, topology=None):
     return Trajectory(xyz, topology, time, box if box.any() else None)
 
 
+XTC_FRAME_DTYPE = np.dtype([("offset", "<i8"), ("nbytes", "<i4"), ("natoms", "<i4"), ("minint", "<i4", 3),
+                            ("maxint", "<i4", 3), ("smallidx", "<i4"), ("precision", "<f4")])
+assert XTC_FRAME_DTYPE.itemsize == _lib.XTC_FRAME_BYTES
+
+
 def read_xtc_device(path, topology=None, device=None):
     """.xtc -> ``Trajectory`` whose coordinates are decoded on the GPU and stay there.
 
-    Only the compressed file image crosses PCIe; ``cgb_xtc_decode`` expands it in HBM."""
+    Only the compressed file image crosses PCIe (read straight into pinned memory, uploaded in blocks of
+    frames while the previous block is being decoded); ``cgb_xtc_decode`` expands it in HBM."""
+    import os
     import torch
     from . import device as dev
     device = device or dev.default_device()
-    image = np.fromfile(path, dtype=np.uint8)
+    size = os.path.getsize(path)
+    pinned = torch.empty(size + 8, dtype=torch.uint8, pin_memory=True)
+    host = pinned.numpy()
+    with open(path, "rb") as handle:
+        got = handle.readinto(memoryview(host)[:size])
+    if got != size:
+        raise OSError(f"'{path}': short read")
+    host[size:] = 0
     try:
-        table, box, time, nf, n_atoms = _scan_xtc(image)
+        table, box, time, nf, n_atoms = _scan_xtc(host[:size])
     except RuntimeError as exc:
         raise OSError(f"'{path}': XTC format is not supported ({exc})") from exc
     _check_topology(topology, n_atoms)
-    padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
-    image_dev = dev.to_device(padded, device)
-    table_dev = dev.to_device(table, device)
     xyz = torch.empty((nf, n_atoms, 3), dtype=torch.float32, device=device)
-    decode_device(image_dev, image.size, table_dev, nf, n_atoms, xyz)
-    torch.cuda.current_stream().synchronize()      # image_dev / table_dev may be released now
+    decode_image_device(pinned, size, table, nf, n_atoms, xyz)
+    torch.cuda.current_stream().synchronize()      # the staging buffers may be released now
     return Trajectory(None, topology, time, box if box.any() else None, xyz_device=xyz)
 
 
-def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, block=4096):
+def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, block_bytes=128 << 20, on_block=None,
+                        image_dev=None, n_streams=4):
+    """Upload an XTC file image from pinned host memory and decode it on the GPU, pipelined: the image goes
+    up in blocks of whole frames (~``block_bytes`` each) on a copy stream, and each block is decoded on one of
+    ``n_streams`` side streams as soon as it has arrived.  A block's decode starts with a sequential walk per
+    frame (a few ms of latency whatever the number of frames), so several blocks are kept in flight to hide
+    it; the upload is then the limit.  ``pinned``: uint8 tensor of the image plus 8 bytes of padding;
+    ``table``: the frame table from ``cgb_xtc_scan`` (numpy uint8).  ``on_block(f0, f1)`` is called with the
+    block's stream current, after the decode of frames [f0, f1) has been enqueued (e.g. to map them right
+    away).  The caller's stream waits for everything on return (asynchronously).  Returns the device image."""
+    import torch
+    from . import device as dev
+    device = xyz_dev.device
+    if image_dev is None:
+        image_dev = torch.empty(n_bytes + 8, dtype=torch.uint8, device=device)
+    table_dev = dev.to_device(table, device)
+    if n_frames == 0:
+        return image_dev
+    recs = table.view(XTC_FRAME_DTYPE)
+    offsets = recs["offset"].astype(np.int64)
+    # block boundaries: frame f1 starts a new block once the block holds >= block_bytes
+    starts = [0]
+    while starts[-1] < n_frames:
+        target = offsets[starts[-1]] + block_bytes
+        nxt = int(np.searchsorted(offsets, target, side="left"))
+        nxt = min(max(nxt, starts[-1] + 1), starts[-1] + 65535, n_frames)
+        starts.append(nxt)
+    main = torch.cuda.current_stream(device)
+    copy = _side_stream(device, "copy")
+    workers = [_side_stream(device, i) for i in range(max(1, min(n_streams, len(starts) - 1)))]
+    entry = torch.cuda.Event()
+    entry.record(main)
+    copy.wait_event(entry)             # buffers may still be in use by earlier work on the caller's stream
+    b0 = 0
+    for k, (f0, f1) in enumerate(zip(starts[:-1], starts[1:])):
+        b1 = int(offsets[f1]) if f1 < n_frames else n_bytes + 8
+        with torch.cuda.stream(copy):
+            image_dev[b0:b1].copy_(pinned[b0:b1], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        worker = workers[k % len(workers)]
+        with torch.cuda.stream(worker):
+            if k < len(workers):
+                worker.wait_event(entry)
+            worker.wait_event(ready)
+            decode_device(image_dev, n_bytes, table_dev, f1 - f0, n_atoms, xyz_dev[f0:], frame0=f0,
+                          workspace_key=k % len(workers))
+            if on_block is not None:
+                on_block(f0, f1)
+        b0 = b1
+    for worker in workers:
+        main.wait_stream(worker)
+    for t in (image_dev, table_dev, xyz_dev):
+        for st in workers + [copy]:
+            t.record_stream(st)
+    return image_dev
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device, name):
+    import torch
+    key = (device.type, device.index, name)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, block=4096, frame0=0, workspace_key=None):
     """``cgb_xtc_decode`` over blocks of frames (one launch handles at most 65535 frames; the
-    checkpoint workspace is sized for one block and reused)."""
+    checkpoint workspace is sized for one block and reused).  Decodes frames [frame0, frame0 + n_frames)
+    of the table into ``xyz_dev[0:n_frames]``."""
     import torch
     from . import device as dev
     lib = _lib.load()
     block = int(min(block, max(n_frames, 1)))
     ws_bytes = int(lib.cgb_xtc_workspace_bytes(block, n_atoms))
-    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz_dev.device)
+    workspace = _workspace(xyz_dev.device, ws_bytes, workspace_key)
     frame_bytes = _lib.XTC_FRAME_BYTES
     for f0 in range(0, n_frames, block):
         f1 = min(n_frames, f0 + block)
-        _lib.check(lib.cgb_xtc_decode(dev.dptr(image_dev), n_bytes, dev.dptr(table_dev[f0 * frame_bytes:]),
+        _lib.check(lib.cgb_xtc_decode(dev.dptr(image_dev), n_bytes, dev.dptr(table_dev[(frame0 + f0) * frame_bytes:]),
                                       f1 - f0, n_atoms, dev.dptr(xyz_dev[f0:]), dev.dptr(workspace), ws_bytes,
                                       dev.stream_handle()), "cgb_xtc_decode")
+
+
+_WORKSPACES = {}
+
+
+def _workspace(device, n_bytes, slot=None):
+    """Decoder scratch, cached per device and pipeline slot (decodes of one slot run in stream order)."""
+    import torch
+    key = (device.type, device.index, slot)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < n_bytes:
+        ws = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
 
 
 def encode_xtc(xyz, unitcell_vectors=None, time=None, precision=1000.0):

@@ -110,6 +110,31 @@ def test_gpu_decoder_on_synthetic_membrane_and_pipeline(tmp_path, options):
 
 
 @pytest.mark.gpu
+def test_pipelined_upload_in_many_blocks(tmp_path):
+    """Blocks of a few frames (upload on the copy stream, decode on the compute stream) give the same floats,
+    and the per-block hook sees every frame exactly once, in order."""
+    import torch
+    from pycgtool_b200 import formats, synth
+    sysm = synth.membrane(4, 60, seed=3)
+    frames = 53
+    image = formats.encode_xtc(sysm.coordinates_host(frames), sysm.box_vectors(frames), precision=1000.0)
+    table, _, _, nf, na = formats._scan_xtc(image)
+    host = np.empty((nf, na, 3), dtype=np.float32)
+    padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
+    from pycgtool_b200 import _lib
+    _lib.check(_lib.load().cgb_xtc_decode_host(_lib.ptr(padded), _lib.ptr(table), nf, na, _lib.ptr(host)))
+    pinned = torch.from_numpy(padded).pin_memory()
+    xyz = torch.full((nf, na, 3), float("nan"), dtype=torch.float32, device="cuda")
+    seen = []
+    formats.decode_image_device(pinned, image.size, table, nf, na, xyz, block_bytes=3 * (image.size // nf),
+                                on_block=lambda f0, f1: seen.append((f0, f1)))
+    torch.cuda.synchronize()
+    assert len(seen) > 5 and seen[0][0] == 0 and seen[-1][1] == nf
+    assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    assert np.array_equal(xyz.cpu().numpy(), host)
+
+
+@pytest.mark.gpu
 def test_frame_device_decode_flag(golden, options):
     from pycgtool_b200 import Frame, Mapping
     frame = Frame(golden / "sugar.gro", golden / "sugar.xtc", device_decode=True)

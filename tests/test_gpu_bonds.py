@@ -317,3 +317,69 @@ def test_frame_shards_merge_to_single_pass(options):
     circ = shards[0]._state.partials[:, 3:5] + shards[1]._state.partials[:, 3:5]
     assert torch.allclose(circ, whole._state.partials[:, 3:5], rtol=2e-6, atol=1e-3)
     assert merged is None or torch.allclose(merged, whole._state.partials[:, :5], rtol=2e-6, atol=1e-3)
+
+
+def _chain_frame(n_beads, xyz, box_len):
+    from pycgtool_b200 import Frame
+    from pycgtool_b200.topology import Topology
+    names = [f"B{i}" for i in range(n_beads)]
+    top = Topology.from_residue_lists([("MOL", names)])
+    n_frames = xyz.shape[0]
+    box = np.zeros((n_frames, 3, 3), dtype=np.float32)
+    box[:, 0, 0] = box[:, 1, 1] = box[:, 2, 2] = box_len
+    lines = ["[ MOL ]"] + [f"{names[i]} {names[i + 1]}" for i in range(n_beads - 1)]
+    lines += [f"{names[i]} {names[i + 1]} {names[i + 2]}" for i in range(n_beads - 2)]
+    lines += [f"{names[i]} {names[i + 1]} {names[i + 2]} {names[i + 3]}" for i in range(n_beads - 3)]
+    return top, Frame.from_arrays(top, xyz, unitcell_vectors=box), box, "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 3, 13, 160])
+def test_degenerate_and_nan_terms_follow_the_reference(options, tmp_path, n_frames):
+    """Coincident beads (length 0, undefined angle), collinear triples, NaN coordinates and images across the
+    box: values equal the oracle's (NaN where it is NaN), statistics skip NaN like np.nanmean / np.nanvar,
+    histograms count what numpy.histogram counts.  Frame counts cover the pair loop, its tail and both."""
+    from pycgtool_b200 import BondSet
+    from pycgtool_b200.bondset import HIST_BINS, HIST_RANGES
+    rng = np.random.default_rng(7 + n_frames)
+    n_beads = 9
+    xyz = (np.arange(n_beads)[None, :, None] * np.array([0.31, 0.07, -0.11]) +
+           rng.normal(0, 0.12, (n_frames, n_beads, 3))).astype(np.float32)
+    xyz[:, 5:] += np.float32(4.7)                    # the chain crosses the periodic boundary (box 5 nm)
+    if n_frames > 2:
+        xyz[2, 1] = xyz[2, 0]                        # coincident beads
+    if n_frames > 5:
+        xyz[5, 3] = np.nan                           # a NaN bead poisons every term it is part of
+        xyz[7, 4:7] = xyz[7, 4] + np.outer(np.arange(3), np.array([0.25, 0.0, 0.0], dtype=np.float32))  # collinear
+        xyz[9] = xyz[8]                              # a repeated frame
+    top, frame, box, bnd_text = _chain_frame(n_beads, xyz, 5.0)
+    bnd = tmp_path / "chain.bnd"
+    bnd.write_text(bnd_text)
+    bondset = BondSet(bnd, options)
+    bondset.apply(frame)
+    bondset.boltzmann_invert()
+    terms = obonds.parse_bnd(bnd, generate_angles=False, generate_dihedrals=False)
+    osys = oracle_system(top, xyz, box)
+    obonds.measure(terms, osys)
+    obonds.invert(terms)
+    hist = bondset._state.hist.cpu().numpy()
+    for k, (bond, term) in enumerate(zip(bondset["MOL"], terms["MOL"])):
+        got, ref = np.asarray(bond.values), np.asarray(term.values)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (bond.atoms, got, ref)
+        ok = ~np.isnan(ref)
+        if len(term.atoms) == 2:
+            assert np.array_equal(got[ok], ref[ok])
+        else:
+            # degenerate geometry (zero-length or collinear operands) is arbitrarily ill-conditioned: compare
+            # the well-defined frames tightly and only require the degenerate ones to be finite where the oracle is
+            diff = np.abs(got[ok].astype(np.float64) - ref[ok].astype(np.float64))
+            diff = np.minimum(diff, 2 * math.pi - diff)
+            regular = np.ones(ok.sum(), dtype=bool)
+            frames_ok = np.flatnonzero(ok)
+            for f in (2, 7):
+                regular &= frames_ok != f
+            assert (diff[regular] < 2e-4).all(), (bond.atoms, diff.max())
+        lo, hi = HIST_RANGES[len(term.atoms)]
+        want, _ = np.histogram(got[~np.isnan(got)].astype(np.float64), bins=HIST_BINS, range=(np.float32(lo), np.float32(hi)))
+        assert np.array_equal(hist[k], want), bond.atoms
+        if n_frames >= 13 and not any(a in ("B0", "B1", "B4", "B5", "B6") for a in term.atoms):
+            _assert_params(bond, term)

@@ -383,3 +383,55 @@ def test_degenerate_and_nan_terms_follow_the_reference(options, tmp_path, n_fram
         assert np.array_equal(hist[k], want), bond.atoms
         if n_frames >= 13 and not any(a in ("B0", "B1", "B4", "B5", "B6") for a in term.atoms):
             _assert_params(bond, term)
+
+
+def test_s3_full_size_properties(options):
+    """Config S3 at its full size (1,048,576 frames, 66 terms): sampled frames equal the oracle, and the
+    size-independent properties hold -- every histogram holds exactly one count per in-range value, the
+    streamed moments equal float64 moments of the stored values, and mapping then measuring a frame shard
+    gives the values of the same frames in the full pass."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200.bondset import HIST_RANGES
+    sysm = synth.small_molecule()
+    n_frames = 1 << 20
+    dev = torch.device("cuda")
+    xyz = sysm.coordinates_device(n_frames, dev, chunk=1 << 14)
+    box = sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    cg = mapper.apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz))
+    bondset = BondSet(bnd_path, options)
+    bondset.apply(cg)
+    bondset.boltzmann_invert()
+    state = bondset._state
+    hist = state.hist.cpu().numpy()
+    partials = state.partials.cpu().numpy()
+    shift = state.shift.cpu().numpy()
+    bonds = bondset["MOL"]
+    assert len(bonds) == 66
+    for k in (0, 11, 22, 23, 40, 44, 45, 60, 65):          # lengths, angles and dihedrals
+        bond = bonds[k]
+        v = np.asarray(bond.values)
+        assert v.shape == (n_frames,) and np.isfinite(v).all()
+        lo, hi = HIST_RANGES[len(bond.atoms)]
+        assert hist[k].sum() == np.count_nonzero((v >= np.float32(lo)) & (v <= np.float32(hi)))
+        assert partials[k, 0] == n_frames
+        if len(bond.atoms) != 4:
+            d = v.astype(np.float64) - np.float64(shift[k])
+            assert partials[k, 1] == pytest.approx(d.sum(), rel=1e-5, abs=1e-3)
+            assert partials[k, 2] == pytest.approx((d * d).sum(), rel=1e-5)
+        if len(bond.atoms) != 2:
+            assert partials[k, 3] == pytest.approx(np.cos(v.astype(np.float64)).sum(), rel=1e-5, abs=0.5)
+            assert partials[k, 4] == pytest.approx(np.sin(v.astype(np.float64)).sum(), rel=1e-5, abs=0.5)
+    # sampled frames against the oracle
+    pick = [0, 1, 77, 4095, 4096, 524287, n_frames - 2, n_frames - 1]
+    sub = xyz[pick].cpu().numpy()
+    ocg = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, sub, box[pick]))
+    terms = obonds.parse_bnd(bnd_path, generate_angles=options.generate_angles,
+                             generate_dihedrals=options.generate_dihedrals)
+    obonds.measure(terms, ocg)
+    for bond, term in zip(bonds, terms["MOL"]):
+        class Sampled:
+            values = np.asarray(bond.values)[pick]
+        _assert_values(Sampled, term, ocg)

@@ -498,7 +498,9 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "impl": "b200",
         "config": {"workload": label, "frames_per_gpu": frames, "n_atoms": n_atoms, "n_beads": n_beads,
-                   "l2": "inputs larger than L2 (18.8 GB per pass), no flush needed",
+                   "l2": "inputs larger than L2 (%.1f GB per pass vs 126 MB), no flush needed" % (bytes_per_launch / 1e9)
+                         if bytes_per_launch > 4 * 126e6 else
+                         "inputs of %.0f MB per pass: comparable to the 126 MB L2 (reduced --frames run)" % (bytes_per_launch / 1e6),
                    "parallelism": f"frame-sharded x{world}, no data-path collective"},
         "roofline": roofline, "clocks": clock_info, "gpu_launches": launches_per_step * args.steps,
     }

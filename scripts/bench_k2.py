@@ -34,6 +34,8 @@ def main():
         print(f"tuning: stage_bytes={sb} stages={ns}")
     if which == "s3":
         sysm, frames = synth.small_molecule(), int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+    elif which == "s5":
+        sysm, frames = synth.s5(), int(sys.argv[2]) if len(sys.argv) > 2 else 16
     else:
         sysm, frames = synth.s5(scale=0.25), int(sys.argv[2]) if len(sys.argv) > 2 else 64
     map_path, bnd_path = sysm.write_files()

@@ -197,7 +197,8 @@ int cgb_boltzmann(const double* partials, const float* shift, const int32_t* nat
 /* ------------------------------------------------------------------------------------------------
  * Trajectory ingest: GROMACS .xtc (the caller of the hot path, reference pycgtool/frame.py:41-63, where the
  * reference calls mdtraj's C codec).  The file image is scanned on the host, the compressed coordinate
- * payloads are decoded on the GPU (one thread per frame) straight into the [F][N][3] float32 trajectory.
+ * payloads are decoded on the GPU (a walk per frame, then one thread per 16 coordinate groups) straight into the
+ * [F][N][3] float32 trajectory.
  * Coordinates are float32(int) * float32(1 / precision), the xdrfile convention.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct CgbXtcFrame {     /* 48 bytes */

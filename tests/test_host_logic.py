@@ -298,3 +298,91 @@ def test_product_never_imports_the_oracle():
     for path in (ROOT / "pycgtool_b200").rglob("*.py"):
         text = path.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+
+
+# ------------------------------------------------------------------------------------------------
+# callers of the hot path: command line surface and force-field writer (no GPU involved)
+# ------------------------------------------------------------------------------------------------
+def test_cli_argument_surface_matches_reference():
+    """reference tests/test_pycgtool.py:56-68 (test_parse_arguments) plus the defaults of
+    pycgtool/__main__.py:149-254 that the hot path reads through the options object."""
+    from pycgtool_b200.__main__ import parse_arguments
+    args = parse_arguments(["TOPOLOGY", "-m", "MAP", "--begin", "1000"])
+    assert args.topology == "TOPOLOGY" and args.trajectory is None
+    assert args.mapping == "MAP" and args.bondset is None and args.begin == 1000 and args.end is None
+    assert (args.map_center, args.virtual_map_center) == ("geom", "geom")
+    assert args.constr_threshold == 100000 and args.temperature == 310 and args.dump_n_values == 10000
+    assert args.generate_angles is True and args.generate_dihedrals is False and args.default_fc is False
+    assert (args.length_form, args.angle_form, args.dihedral_form) == ("Harmonic", "CosHarmonic", "Harmonic")
+    assert args.output_xtc is False and args.output_forcefield is False and args.dump_measurements is False
+    flipped = parse_arguments(["T", "X", "-b", "BND", "--no-generate-angles", "--generate-dihedrals", "--output-xtc"])
+    assert flipped.trajectory == "X" and flipped.generate_angles is False and flipped.generate_dihedrals is True
+    assert flipped.output_xtc is True
+    # a bond file without a mapping means "measure only": samples are dumped (__main__.py:257-276)
+    assert flipped.dump_measurements is True
+    with pytest.raises(SystemExit):
+        parse_arguments(["TOPOLOGY"])          # one of -m / -b is required
+
+
+def test_forcefield_rtp_r2b_from_golden_parameters(golden, options, tmp_path):
+    """`.rtp` / `.r2b` text of the reference's force-field test (tests/test_pycgtool.py:175-212): the bonded
+    parameters are injected from the oracle-pinned fixture, so this covers the writer alone."""
+    import json
+    from pycgtool_b200 import BondSet, Mapping
+    from pycgtool_b200.forcefield import ForceField
+    from pycgtool_b200.util import cmp_file_whitespace_float
+    mapping = Mapping(golden / "sugar.map", options)
+    bonds = BondSet(golden / "sugar.bnd", options)
+    stored = json.loads((golden / "sugar_params.json").read_text())
+    for bond, rec in zip(bonds["ALLA"], stored):
+        assert list(bond.atoms) == rec["atoms"]
+        bond.eqm, bond.fconst = rec["eqm"], rec["fconst"]
+    ff = ForceField("out", dir_path=tmp_path)
+    ff.write("out", mapping, bonds)
+    out = tmp_path / "ffout.ff"
+    assert cmp_file_whitespace_float(golden / "ffout.ff" / "out.rtp", out / "out.rtp", rtol=1e-6, verbose=True)
+    assert (out / "out.r2b").read_text() == (golden / "ffout.ff" / "out.r2b").read_text()
+    assert (out / "forcefield.itp").read_text().splitlines()[0] == "#define _FF_PYCGTOOL_out"
+    # a second writer backs the directory up instead of overwriting it (util.backup_file)
+    ForceField("out", dir_path=tmp_path)
+    assert any(p.name.startswith("#ffout.ff") for p in tmp_path.iterdir())
+
+
+def test_forcefield_terminal_residue_variants():
+    """Bonds reaching into the neighbouring residue ('+' / '-' prefixes) produce N- / C- / 2-terminal building
+    blocks and the matching .r2b table (pycgtool/forcefield.py:118-212)."""
+    from pycgtool_b200.forcefield import ForceField
+
+    class FakeBond:
+        def __init__(self, atoms):
+            self.atoms, self.eqm, self.fconst = atoms, 1.0, 100.0
+
+        def __iter__(self):
+            return iter(self.atoms)
+
+    class FakeBonds:
+        def __init__(self, table):
+            self.table = table
+
+        def get_bonds(self, mol, natoms, select=lambda x: True):
+            bonds = self.table[mol]
+            if natoms != -1:
+                bonds = [b for b in bonds if len(b.atoms) == natoms]
+            return [b for b in bonds if select(b)]
+
+    class Bead:
+        def __init__(self, name):
+            self.name, self.type, self.charge = name, "P1", 0.0
+
+    mapping = {"ETH": [Bead("C1"), Bead("C2")]}
+    bonds = FakeBonds({"ETH": [FakeBond(["C1", "C2"]), FakeBond(["C2", "+C1"]), FakeBond(["-C2", "C1", "C2"])]})
+    lines, nterms, cterms = ForceField.write_rtp(mapping, bonds)
+    assert nterms == {"ETH"} and cterms == {"ETH"}
+    text = "\n".join(lines)
+    for block in ("[ ETH ]", "[ NETH ]", "[ CETH ]", "[ 2ETH ]"):
+        assert block in text
+    n_block = text.split("[ NETH ]")[1].split("[ CETH ]")[0]
+    assert "-C2" not in n_block and "+C1" in n_block
+    two_block = text.split("[ 2ETH ]")[1]
+    assert "-C2" not in two_block and "+C1" not in two_block and "C1   C2" in two_block
+    assert ForceField.write_r2b(nterms, cterms)[-1].split() == ["ETH", "ETH", "NETH", "CETH", "2ETH"]

@@ -96,6 +96,26 @@ class VirtualMap(BeadMap):
         return
 
 
+def _unique_rows(block):
+    """Distinct rows of an integer matrix and, per row, the index of its distinct row.
+
+    ``np.unique(axis=0)`` sorts the rows lexicographically (9 s for the 20 M-atom configuration); hashing each
+    row to 64 bits and sorting the hashes is ~30x faster.  Collisions are detected and fall back."""
+    n, width = block.shape
+    if n == 0 or width == 0:
+        return block[:1], np.zeros(n, dtype=np.int64)
+    mult = (np.arange(1, width + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        hashed = (block.astype(np.uint64) * mult[None, :]).sum(axis=1, dtype=np.uint64)
+    _, first, inverse = np.unique(hashed, return_index=True, return_inverse=True)
+    templates = block[first]
+    inverse = inverse.reshape(-1)
+    if not np.array_equal(templates[inverse], block):      # two different rows with one hash
+        templates, inverse = np.unique(block, axis=0, return_inverse=True)
+        inverse = inverse.reshape(-1)
+    return templates, inverse
+
+
 class MapPlan:
     """Integer tables for one (mapping, topology) pair; everything frame-invariant."""
 
@@ -305,8 +325,7 @@ class Mapping:
                     block = top.atom_name_id[firsts[:, None] + np.arange(natoms)[None, :]]
                 else:
                     block = np.zeros((len(sel), 0), dtype=np.int32)
-                templates, inverse = np.unique(block, axis=0, return_inverse=True)
-                inverse = inverse.reshape(-1)
+                templates, inverse = _unique_rows(block)
                 for t, template in enumerate(templates):
                     atom_names = [top.atom_names[a] for a in template]
                     members = sel[inverse == t]

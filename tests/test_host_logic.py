@@ -386,3 +386,15 @@ def test_forcefield_terminal_residue_variants():
     two_block = text.split("[ 2ETH ]")[1]
     assert "-C2" not in two_block and "+C1" not in two_block and "C1   C2" in two_block
     assert ForceField.write_r2b(nterms, cterms)[-1].split() == ["ETH", "ETH", "NETH", "CETH", "2ETH"]
+
+
+def test_unique_rows_matches_numpy():
+    from pycgtool_b200.mapping import _unique_rows
+    rng = np.random.default_rng(0)
+    pool = rng.integers(0, 50, size=(7, 12)).astype(np.int32)
+    block = pool[rng.integers(0, 7, size=5000)]
+    templates, inverse = _unique_rows(block)
+    assert np.array_equal(templates[inverse], block)
+    assert len(templates) == len(np.unique(block, axis=0))
+    empty, inv = _unique_rows(np.zeros((4, 0), dtype=np.int32))
+    assert len(inv) == 4 and (inv == 0).all()

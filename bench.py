@@ -363,6 +363,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from pycgtool_b200 import device as cgb_device
+    cpus = cgb_device.bind_host_to_gpu(local) if world > 1 else None     # NUMA-local pinned buffers per rank
     if world > 1:
         # stdout carries exactly one JSON line: NCCL prints its version banner there when the communicator
         # is created, so file descriptor 1 points at stderr until the first collective has run
@@ -501,7 +503,9 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (%.1f GB per pass vs 126 MB), no flush needed" % (bytes_per_launch / 1e9)
                          if bytes_per_launch > 4 * 126e6 else
                          "inputs of %.0f MB per pass: comparable to the 126 MB L2 (reduced --frames run)" % (bytes_per_launch / 1e6),
-                   "parallelism": f"frame-sharded x{world}, no data-path collective"},
+                   "parallelism": f"frame-sharded x{world}, no data-path collective",
+                   "host_binding": (f"rank bound to the {len(cpus)} CPU cores local to its GPU (NVML)" if cpus else
+                                    "none")},
         "roofline": roofline, "clocks": clock_info, "gpu_launches": launches_per_step * args.steps,
     }
     if e2e is not None:

@@ -52,3 +52,25 @@ def dptr(tensor):
     if not tensor.is_contiguous():
         raise ValueError("tensor must be contiguous")
     return tensor.data_ptr()
+
+
+def bind_host_to_gpu(index=None):
+    """Pin the calling process to the CPU cores NVML reports as local to the GPU (its NUMA node), so that
+    pinned staging buffers allocated afterwards land in memory next to the GPU's PCIe root.  With one
+    process per GPU this keeps eight concurrent host<->device streams off a single memory controller.
+    Best effort: returns the CPU set, or None when NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = torch.cuda.current_device() if index is None else index
+        props = torch.cuda.get_device_properties(index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except (AttributeError, pynvml.NVMLError):
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:                      # noqa: BLE001 -- purely an optimisation
+        return None

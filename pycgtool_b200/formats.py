@@ -34,6 +34,7 @@ def read_gro(path):
     natoms = int(text[1])
     body = text[2:2 + natoms]
     residues, last = [], None
+    res_seq, serial = [], []
     xyz = np.empty((1, natoms, 3), dtype=np.float32)
     if natoms:
         dots = [i for i, ch in enumerate(body[0]) if ch == "." and i >= 20]
@@ -43,7 +44,9 @@ def read_gro(path):
         if key != last:
             resname = RESIDUE_NAME_REPLACEMENTS.get(line[5:10].strip(), line[5:10].strip())
             residues.append((resname, []))
+            res_seq.append(int(line[0:5]))
             last = key
+        serial.append(int(line[15:20]))
         resname = residues[-1][0]
         atom = line[10:15].strip()
         residues[-1][1].append(ATOM_NAME_REPLACEMENTS.get(resname, {}).get(atom, atom))
@@ -55,21 +58,70 @@ def read_gro(path):
     if len(fields) == 9:
         box[0, 0, 1], box[0, 0, 2], box[0, 1, 0], box[0, 1, 2], box[0, 2, 0], box[0, 2, 1] = fields[3:]
     top = Topology.from_residue_lists(residues)
+    top.res_seq, top.atom_serial = np.array(res_seq, dtype=np.int64), np.array(serial, dtype=np.int64)
     return Trajectory(xyz, top, np.zeros(1, dtype=np.float32), box if box.any() else None)
 
 
+def read_pdb(path):
+    """First model of a .pdb -> ``Trajectory`` (Angstrom -> nm, float32).  Fixed-column ATOM / HETATM
+    records and CRYST1; residues change with (chain, resSeq, iCode, resName).  A CRYST1 with zero
+    lengths means "no box", as mdtraj treats it."""
+    residues, last, coords = [], None, []
+    box = None
+    with open(path) as handle:
+        for line in handle:
+            rec = line[:6]
+            if rec == "CRYST1":
+                a, b, c = (float(line[6 + 9 * k:15 + 9 * k]) / 10.0 for k in range(3))
+                angles = [float(line[33 + 7 * k:40 + 7 * k]) for k in range(3)]
+                if a > 0 and b > 0 and c > 0:
+                    box = _box_from_lengths_angles(a, b, c, *angles)
+            elif rec in ("ATOM  ", "HETATM"):
+                key = (line[21], line[22:27], line[17:21].strip())
+                if key != last:
+                    resname = RESIDUE_NAME_REPLACEMENTS.get(key[2], key[2])
+                    residues.append((resname, []))
+                    last = key
+                resname = residues[-1][0]
+                atom = line[12:16].strip()
+                residues[-1][1].append(ATOM_NAME_REPLACEMENTS.get(resname, {}).get(atom, atom))
+                coords.append([float(line[30:38]) / 10.0, float(line[38:46]) / 10.0, float(line[46:54]) / 10.0])
+            elif rec == "ENDMDL":
+                break
+    if not coords:
+        raise OSError(f"'{path}': PDB format is not supported (no ATOM records)")
+    xyz = np.asarray(coords, dtype=np.float32)[None]
+    top = Topology.from_residue_lists(residues)
+    return Trajectory(xyz, top, np.zeros(1, dtype=np.float32), None if box is None else box[None])
+
+
+def _box_from_lengths_angles(a, b, c, alpha, beta, gamma):
+    """Row vectors of the cell (mdtraj.utils.lengths_and_angles_to_box_vectors)."""
+    alpha, beta, gamma = np.radians([alpha, beta, gamma])
+    va = [a, 0.0, 0.0]
+    vb = [b * np.cos(gamma), b * np.sin(gamma), 0.0]
+    cx = c * np.cos(beta)
+    cy = c * (np.cos(alpha) - np.cos(beta) * np.cos(gamma)) / np.sin(gamma)
+    cz = np.sqrt(max(c * c - cx * cx - cy * cy, 0.0))
+    box = np.array([va, vb, [cx, cy, cz]], dtype=np.float64)
+    box[np.abs(box) < 1e-6 * max(a, b, c)] = 0.0
+    return box.astype(np.float32)
+
+
 def write_gro(path, traj, frame=0):
-    """Write one frame in mdtraj's .gro dialect (zero-based numbering for
-    topologies built in memory, 3 decimals, always nine box fields)."""
+    """Write one frame in mdtraj's .gro dialect (the file's own numbering for topologies read from a
+    file, zero-based for topologies built in memory; 3 decimals, always nine box fields)."""
     top = traj.topology
     xyz = traj.xyz[frame]
+    res_seq = top.res_seq if top.res_seq is not None else np.arange(top.n_residues)
+    serial = top.atom_serial if top.atom_serial is not None else np.arange(top.n_atoms)
     lines = ["Generated with MDTraj, t= %s" % float(traj.time[frame]), " %d" % top.n_atoms]
     res_of_atom = np.repeat(np.arange(top.n_residues), np.diff(top.res_first))
     for i in range(top.n_atoms):
         r = int(res_of_atom[i])
         lines.append("%5d%-5s%5s%5d%8.3f%8.3f%8.3f" % (
-            r % 100000, top.res_names[top.res_name_id[r]], top.atom_names[top.atom_name_id[i]],
-            i % 100000, xyz[i, 0], xyz[i, 1], xyz[i, 2]))
+            int(res_seq[r]) % 100000, top.res_names[top.res_name_id[r]], top.atom_names[top.atom_name_id[i]],
+            int(serial[i]) % 100000, xyz[i, 0], xyz[i, 1], xyz[i, 2]))
     v = traj.unitcell_vectors
     b = np.zeros((3, 3)) if v is None else v[frame]
     lines.append(("%10.5f" * 9) % (b[0, 0], b[1, 1], b[2, 2], b[0, 1], b[0, 2], b[1, 0], b[1, 2], b[2, 0], b[2, 1]))
@@ -281,6 +333,8 @@ def load(path, top=None, on_device=False):
     suffix = str(path).lower().rsplit(".", 1)[-1]
     if suffix == "gro":
         return read_gro(path)
+    if suffix == "pdb":
+        return read_pdb(path)
     if suffix == "xtc":
         return read_xtc_device(path, top) if on_device else read_xtc(path, top)
     raise OSError(f"'{path}': format is not supported")

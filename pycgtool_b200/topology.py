@@ -50,6 +50,12 @@ class Atom:
     def __repr__(self):
         return f"<Atom {self.index} {self.name}>"
 
+    def __eq__(self, other):       # views are created on demand: identity is (topology, index)
+        return isinstance(other, Atom) and other._top is self._top and other.index == self.index
+
+    def __hash__(self):
+        return hash((id(self._top), "atom", self.index))
+
 
 class Residue:
     """View of one residue: a contiguous run of atoms."""
@@ -67,6 +73,12 @@ class Residue:
     @property
     def n_atoms(self):
         return int(self._top.res_first[self.index + 1] - self._top.res_first[self.index])
+
+    def __eq__(self, other):       # views are created on demand: identity is (topology, index)
+        return isinstance(other, Residue) and other._top is self._top and other.index == self.index
+
+    def __hash__(self):
+        return hash((id(self._top), "residue", self.index))
 
     @property
     def atoms(self):
@@ -104,6 +116,10 @@ class Topology:
         self.res_name_id = np.zeros(0, dtype=np.int32)  # (R,)
         self.res_first = np.zeros(1, dtype=np.int64)    # (R+1,) first atom of each residue
         self.atom_name_id = np.zeros(0, dtype=np.int32) # (N,)
+        # numbering as read from a file (mdtraj's residue.resSeq / atom.serial); None for topologies built in
+        # memory, which mdtraj numbers from zero when it writes them
+        self.res_seq = None
+        self.atom_serial = None
         self._owner = None
         self._pending_coords = {}
         self._grow_res, self._grow_first, self._grow_atoms = None, None, None

@@ -170,3 +170,24 @@ def any_starts_with(iterable, char):
     if isinstance(iterable, str):
         return iterable.startswith(char)
     return any(any_starts_with(item, char) for item in iterable)
+
+
+def compare_trajectories(*trajectory_files, topology_file=None, rtol=0.001):
+    """Compare trajectories for equality (``pycgtool/util.py:268-318``): same atom count, coordinates within
+    ``rtol``, same box.  Returns True, raises ``ValueError`` describing the first difference."""
+    from . import formats
+    top = None if topology_file is None else formats.load(topology_file).topology
+    ref = formats.load(trajectory_files[0], top=top)
+    for other_file in trajectory_files[1:]:
+        try:
+            other = formats.load(other_file, top=top)
+        except ValueError as exc:
+            raise ValueError("Topology does not match") from exc
+        if other.n_atoms != ref.n_atoms or other.n_frames != ref.n_frames:
+            raise ValueError("Number of atoms or frames does not match")
+        if not np.allclose(other.xyz, ref.xyz, rtol=rtol):
+            raise ValueError("Coordinates do not match")
+        a, b = ref.unitcell_lengths, other.unitcell_lengths
+        if (a is None) != (b is None) or (a is not None and not np.allclose(a, b, rtol=rtol)):
+            raise ValueError("Unitcell does not match")
+    return True

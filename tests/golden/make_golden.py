@@ -25,7 +25,7 @@ COPIES = [
     "sugar_out.gro", "sugar_only.map",
     "ALLA_length.dat", "ALLA_angle.dat", "ALLA_dihedral.dat",
     "ALLA_length_one.dat", "ALLA_angle_one.dat", "ALLA_dihedral_one.dat",
-    "water.gro", "water.xtc", "water.map", "water_double_weight.map", "water-cg.gro", "pbcwater.gro",
+    "water.gro", "water.xtc", "water.pdb", "water-nobox.pdb", "water.map", "water_double_weight.map", "water-cg.gro", "pbcwater.gro",
     "two.gro", "two.map", "two.itp", "dppc.map",
     "polyethene.gro", "polyethene.bnd", "polyethene.map", "pbcpolyethene.gro",
     "triangle.bnd", "duplicate_atoms.bnd", "twice.cfg", "nosections.cfg",

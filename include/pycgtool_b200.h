@@ -143,7 +143,7 @@ int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
  * col_slot[c] is the number of column c's Bond; max_slots is the largest count over all groups.  It lets a
  * CTA keep its per-Bond sums and histograms in shared memory sized by the group, not by the system.
  * NULL (or max_slots too large for shared memory) selects global atomics. */
-#define CGB_MEASURE_TILE 256
+#define CGB_MEASURE_TILE 224
 /* tile_span: device int32 [T][2] or NULL, T = sum over kinds of ceil(n_kind / CGB_MEASURE_TILE), one row per
  * group in kind order: (first bead, number of beads) of the contiguous bead range that contains every bead
  * of the group's columns; max_span = the largest number of beads.  With tile_span (and col_slot) the staged

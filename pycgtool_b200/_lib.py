@@ -11,7 +11,7 @@ _CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIBRARY_PATH = _CSRC / "libpycgtool_b200.so"
 
 NPART = 8  # CGB_NPART
-MEASURE_TILE = 256  # CGB_MEASURE_TILE
+MEASURE_TILE = 224  # CGB_MEASURE_TILE
 
 FORM_IDS = {
     "Harmonic": 0,

@@ -17,7 +17,9 @@ N = 156,672 atoms -> B = 13,824 MARTINI beads, 10,000 frames, synthetic coordina
                  F*(12N + 12B + 12) per launch / CUDA-event duration, against MEASURED_PEAKS.json.
 * ``cpu_baseline`` the oracle (NumPy restatement of the reference, its loop structure kept) timed on
                  the host cores on a bounded frame sample.
-* ``measure``    supplementary: bonded-term measurement (K2) on config S3 (1 M frames, 66 terms).
+* ``measure``    supplementary: bonded-term measurement (K2) on config S3 (1 M frames, 66 terms);
+                 ``measure_membrane``: the same on a quarter-size S5 membrane; ``ingest``: compressed
+                 .xtc image -> GPU decode -> mapping -> beads on the host.
 
 Multi-GPU (torchrun, one rank per GPU): frames are independent, so every rank maps its own
 10,000-frame shard with no data-path collective (weak scaling); value = all atom-frames / max time.
@@ -213,8 +215,9 @@ def cpu_baseline_leg(sysm, map_path, frames_total, sample_frames=512):
                       f"best of 2, host has {os.cpu_count()} cores"}
 
 
-def measure_leg(dev, peak_gbs):
-    """Supplementary: K2 (bond measurement + statistics) on config S3, device resident.
+def measure_leg(dev, peak_gbs, workload="s3"):
+    """Supplementary: K2 (bond measurement + statistics), device resident, on config S3 or on a
+    quarter-size S5 membrane (many instances per Bond, tiles of 224 columns).
 
     `value` times the three `measure_kernel` launches of one `cgb_measure` call (values + moments +
     circular sums + 128-bin histograms); `api_ms_per_pass` is `BondSet.apply` as a user calls it
@@ -223,10 +226,14 @@ def measure_leg(dev, peak_gbs):
     from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth
     from pycgtool_b200.synth import Options
     lib = _lib.load()
-    sysm = synth.small_molecule()
-    n_frames = 1 << 20
+    if workload == "s3":
+        sysm, n_frames, chunk = synth.small_molecule(), 1 << 20, 1 << 16
+        label = "S3 small molecule: 24 beads, 66 terms (23 bonds, 22 angles, 21 dihedrals), 1,048,576 frames"
+    else:
+        sysm, n_frames, chunk = synth.s5(scale=0.25), 256, 8
+        label = "quarter-size S5 membrane (5M atoms), 256 frames"
     map_path, bnd_path = sysm.write_files()
-    xyz = sysm.coordinates_device(n_frames, dev, chunk=1 << 16)
+    xyz = sysm.coordinates_device(n_frames, dev, chunk=chunk)
     box = sysm.box_vectors(n_frames)
     mapper = Mapping(map_path, Options())
     cg = mapper.apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz))
@@ -279,9 +286,11 @@ def measure_leg(dev, peak_gbs):
     touched = len(np.unique(plan.col_beads))
     bytes_alg = n_frames * (12 * touched + 4 * n_terms + 36)   # 12 B per bead touched
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    return {"workload": "S3 small molecule: 24 beads, 66 terms (23 bonds, 22 angles, 21 dihedrals), 1,048,576 frames",
+    if workload != "s3":
+        label += f": {plan.n_beads:,} beads, {n_terms:,} terms per frame ({n2:,} bonds, {n3:,} angles, {n4:,} dihedrals)"
+    return {"workload": label,
             "value": measures / (ms * 1e-3), "unit": "bond-measures/s", "ms_per_pass": ms,
-            "includes": "values + moments + circular sums + 128-bin histograms (3 measure_tiles_kernel launches)",
+            "includes": "values + moments + circular sums + 128-bin histograms (one measure_tiles_kernel launch per kind)",
             "api_ms_per_pass": api_ms, "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs,
             "frac_of_hbm_peak": gbs / peak_gbs, "bound": "instruction issue (acos/atan2 per measure), not HBM",
             "boltzmann_invert_ms": invert_ms}
@@ -516,6 +525,7 @@ def run_b200(args):
         line["cpu_baseline"] = cpu_baseline_leg(sysm, map_path, frames)
         try:
             line["measure"] = measure_leg(dev, peak_gbs)
+            line["measure_membrane"] = measure_leg(dev, peak_gbs, "membrane")
         except Exception as exc:  # supplementary leg must not take the headline down
             line["measure"] = {"error": repr(exc)}
         if args.workload == "s2":

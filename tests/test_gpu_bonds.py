@@ -435,3 +435,45 @@ def test_s3_full_size_properties(options):
         class Sampled:
             values = np.asarray(bond.values)[pick]
         _assert_values(Sampled, term, ocg)
+
+
+def test_s5_size_sampled_terms(options):
+    """Largest configuration (S5, 1.7 M beads, 79 kinds of residue, 4 frames): for every Bond a handful of
+    instances spread over the system is measured by the oracle on the same CG coordinates -- lengths bit-exact,
+    angles within the float32 acos / atan2 conditioning -- and every value buffer has the reference's length."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    sysm = synth.s5()
+    n_frames = 4
+    dev = torch.device("cuda")
+    xyz = sysm.coordinates_device(n_frames, dev, chunk=1)
+    box = sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz))
+    del xyz
+    bondset = BondSet(bnd_path, options)
+    bondset.apply(cg)
+    plan = bondset._state.plan
+    cg_xyz = cg._trajectory.xyz                                # (F, B, 3) on the host
+    rng = np.random.default_rng(11)
+    import itertools
+    bonds = list(itertools.chain(*bondset._molecules.values()))
+    assert len(bonds) == plan.n_bonds and plan.n_bonds >= 79
+    checked = 0
+    for k, bond in enumerate(bonds):
+        table = plan.bond_indices[k]
+        n_inst = len(table)
+        if n_inst == 0:
+            continue
+        values = np.asarray(bond.values).reshape(n_frames, n_inst)
+        pick = np.unique(np.concatenate([[0, n_inst - 1], rng.integers(0, n_inst, 6)]))
+        ref = ogeom.MEASURE[len(bond.atoms)](cg_xyz, table[pick].astype(np.int64), box)
+        got = values[:, pick]
+        if len(bond.atoms) == 2:
+            assert np.array_equal(got, ref), bond.atoms
+        else:
+            diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+            tol = ANGLE_ABS + COS_ULPS / np.maximum(np.sin(ref.astype(np.float64)), 1e-3)
+            assert (diff <= tol).all(), (bond.atoms, float(diff.max()))
+        checked += got.size
+    assert checked > 79 * 4 * 4

@@ -262,3 +262,44 @@ def test_s2_shape_sampled_frames(options):
     # size-independent property: with geometric weights and unwrapping, every bead lies within
     # the spread of its atoms around the reference atom -> finite and inside an enlarged box
     assert torch.isfinite(got).all()
+
+
+def test_s5_size_sampled_beads(options):
+    """Largest configuration (S5: 19,999,992 atoms -> 1,710,442 beads, 79 residue kinds), two frames generated
+    on the device: 4,000 beads sampled over the whole system are recomputed with the oracle's bead expression
+    (reference atom first, minimum image with box lengths, un-fused float32 sum in atom order) and must match
+    bit for bit; the assignment tables they use were checked against the oracle's on the CPU."""
+    import torch
+    from oracle import mapping as omap
+    from pycgtool_b200 import Frame, Mapping, synth
+    sysm = synth.s5()
+    assert sysm.n_atoms == 19999992
+    n_frames = 2
+    dev = torch.device("cuda")
+    xyz = sysm.coordinates_device(n_frames, dev, chunk=1)
+    box = sysm.box_vectors(n_frames)
+    map_path, _ = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    cg = mapper.apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz))
+    plan = mapper._plan_for(sysm.topology)
+    assert cg.natoms == plan.n_beads == 1710442
+    got = cg._trajectory.device_xyz()
+    assert torch.isfinite(got).all()
+    rng = np.random.default_rng(5)
+    beads = np.unique(np.concatenate([rng.integers(0, plan.n_beads, 3990), [0, 1, plan.n_beads - 2, plan.n_beads - 1]]))
+    lengths = np.stack([box[:, 0, 0], box[:, 1, 1], box[:, 2, 2]], axis=1).astype(np.float32)
+    host = {}
+    for b in beads:
+        atoms = plan.index[plan.bead_ptr[b]:plan.bead_ptr[b + 1]]
+        for a in atoms:
+            host[int(a)] = None
+    wanted = torch.tensor(sorted(host), device=dev)
+    coords = xyz[:, wanted].cpu().numpy()
+    where = {a: i for i, a in enumerate(sorted(host))}
+    out = got[:, torch.tensor(beads, device=dev)].cpu().numpy()
+    for k, b in enumerate(beads):
+        lo, hi = plan.bead_ptr[b], plan.bead_ptr[b + 1]
+        sel = [where[int(a)] for a in plan.index[lo:hi]]
+        atom_xyz = np.ascontiguousarray(coords[:, sel].transpose(1, 0, 2))          # (atoms, frames, 3)
+        ref = omap.calc_coords_weight(atom_xyz[0], atom_xyz, plan.weights[lo:hi], lengths)
+        assert np.array_equal(out[:, k], ref.astype(np.float32)), int(b)

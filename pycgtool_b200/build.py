@@ -21,7 +21,7 @@ STAMP = CSRC / ".build_stamp"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
 ]
 
 

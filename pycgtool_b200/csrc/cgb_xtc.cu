@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "cgb_common.cuh"
@@ -567,20 +569,45 @@ extern "C" int cgb_xtc_scan(const uint8_t* data, int64_t n_bytes, int64_t max_fr
     return CGB_OK;
 }
 
+namespace cgb {
+
+// Run fn(f) for f in [0, n) on the host cores (frames of a trajectory are independent).
+template <class Fn>
+static void parallel_frames(int64_t n, Fn fn) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int64_t workers = std::min<int64_t>(std::min<int64_t>(hw, 64), n);
+    if (workers <= 1) {
+        for (int64_t f = 0; f < n; ++f) fn(f);
+        return;
+    }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)workers);
+    for (int64_t w = 0; w < workers; ++w)
+        pool.emplace_back([&]() {
+            for (int64_t f = next.fetch_add(1); f < n; f = next.fetch_add(1)) fn(f);
+        });
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace cgb
+
 extern "C" int cgb_xtc_decode_host(const uint8_t* data, const CgbXtcFrame* frames, int64_t n_frames,
                                    int64_t n_atoms, float* xyz) {
     using namespace cgb;
     if (n_frames < 0 || n_atoms < 0) return CGB_EINVAL;
     if (n_frames == 0) return CGB_OK;
     if (!data || !frames || !xyz) return CGB_EINVAL;
-    for (int64_t f = 0; f < n_frames; ++f) {
+    for (int64_t f = 0; f < n_frames; ++f)
         if (frames[f].natoms != n_atoms) return CGB_EINVAL;
+    // frames are independent: decode them on all host cores
+    parallel_frames(n_frames, [&](int64_t f) {
         float* out = xyz + (size_t)f * n_atoms * 3;
         if (frames[f].natoms <= 9)
             decode_raw(data + frames[f].offset, frames[f].natoms, out);
         else
             decode_frame(data + frames[f].offset, frames[f], out);
-    }
+    });
     return CGB_OK;
 }
 
@@ -614,26 +641,22 @@ extern "C" int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtc
 
 // Encode frames into a caller-provided buffer; returns the bytes written through *n_written, or
 // CGB_ERANGE when `capacity` is too small (call again with a larger buffer).
-extern "C" int cgb_xtc_encode(const float* xyz, const float* box, const float* time, int64_t n_frames,
-                              int64_t n_atoms, float precision, uint8_t* out, int64_t capacity,
-                              int64_t* n_written) {
-    using namespace cgb;
-    if (n_frames < 0 || n_atoms < 0 || !n_written || (n_frames && n_atoms && !xyz) || precision <= 0)
-        return CGB_EINVAL;
-    std::vector<uint8_t> buf;
-    buf.reserve((size_t)std::min<int64_t>(capacity > 0 ? capacity : 1 << 20, (int64_t)1 << 30));
+namespace cgb {
+
+// One frame (header + compressed coordinates) appended to `buf`; CGB_OK or CGB_ERANGE.
+static int encode_frame(const float* x, const float* box9, float time, int64_t f, int64_t n_atoms, float precision,
+                        std::vector<uint8_t>& buf) {
     std::vector<int> ip((size_t)n_atoms * 3);
-    for (int64_t f = 0; f < n_frames; ++f) {
-        const float* x = xyz + (size_t)f * n_atoms * 3;
+    {
         put_be32(buf, 1995);
         put_be32(buf, (uint32_t)n_atoms);
         put_be32(buf, (uint32_t)f);
-        put_bef(buf, time ? time[f] : (float)f);
-        for (int k = 0; k < 9; ++k) put_bef(buf, box ? box[f * 9 + k] : 0.0f);
+        put_bef(buf, time);
+        for (int k = 0; k < 9; ++k) put_bef(buf, box9 ? box9[k] : 0.0f);
         put_be32(buf, (uint32_t)n_atoms);
         if (n_atoms <= 9) {
             for (int64_t i = 0; i < 3 * n_atoms; ++i) put_bef(buf, x[i]);
-            continue;
+            return CGB_OK;
         }
         int minint[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, maxint[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
         for (int64_t i = 0; i < n_atoms; ++i)
@@ -731,8 +754,35 @@ extern "C" int cgb_xtc_encode(const float* xyz, const float* box, const float* t
         buf.insert(buf.end(), payload.begin(), payload.end());
         while (buf.size() % 4) buf.push_back(0);
     }
-    *n_written = (int64_t)buf.size();
-    if ((int64_t)buf.size() > capacity || (!out && !buf.empty())) return CGB_ERANGE;
-    if (!buf.empty()) memcpy(out, buf.data(), buf.size());
+    return CGB_OK;
+}
+
+}  // namespace cgb
+
+extern "C" int cgb_xtc_encode(const float* xyz, const float* box, const float* time, int64_t n_frames,
+                              int64_t n_atoms, float precision, uint8_t* out, int64_t capacity,
+                              int64_t* n_written) {
+    using namespace cgb;
+    if (n_frames < 0 || n_atoms < 0 || !n_written || (n_frames && n_atoms && !xyz) || precision <= 0)
+        return CGB_EINVAL;
+    // frames are independent: encode them on all host cores, then concatenate
+    std::vector<std::vector<uint8_t>> parts((size_t)n_frames);
+    std::vector<int> status((size_t)n_frames, CGB_OK);
+    parallel_frames(n_frames, [&](int64_t f) {
+        status[(size_t)f] = encode_frame(xyz + (size_t)f * n_atoms * 3, box ? box + f * 9 : nullptr,
+                                         time ? time[f] : (float)f, f, n_atoms, precision, parts[(size_t)f]);
+    });
+    size_t total = 0;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        if (status[(size_t)f] != CGB_OK) return status[(size_t)f];
+        total += parts[(size_t)f].size();
+    }
+    *n_written = (int64_t)total;
+    if ((int64_t)total > capacity || (!out && total)) return CGB_ERANGE;
+    size_t at = 0;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        if (!parts[(size_t)f].empty()) memcpy(out + at, parts[(size_t)f].data(), parts[(size_t)f].size());
+        at += parts[(size_t)f].size();
+    }
     return CGB_OK;
 }

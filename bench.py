@@ -357,7 +357,7 @@ def ingest_leg(sysm, mapper, plan, dev, frames=2048):
             "value": nf * n_atoms / dt, "unit": "atom-frames/s", "frames": nf, "ms": dt * 1e3,
             "compressed_bytes_per_atom": len(image) / nf / n_atoms, "h2d_bytes": int(len(image)),
             "gpu_decode_atoms_per_s": nf * n_atoms / (start.elapsed_time(stop) * 1e-3),
-            "host_decode_atoms_per_s_1core": host_rate,
+            "host_decode_atoms_per_s": host_rate, "host_decode_cores": os.cpu_count(),
             "note": "decode = per-frame walk over a shared-memory ring (one warp per frame, all frames of a block "
                     "concurrently) + parallel decode of checkpoints; upload of block i+1 overlaps decode of block i"}
 

@@ -27,14 +27,14 @@ def main():
     image = formats.encode_xtc(xyz, box, precision=1000.0)
     t_enc = time.perf_counter() - t0
     n_atoms = sysm.n_atoms
-    print(f"encode (host, 1 core): {frames * n_atoms / t_enc:.3e} atoms/s, {len(image) / frames / n_atoms:.2f} B/atom")
+    print(f"encode (host, all cores): {frames * n_atoms / t_enc:.3e} atoms/s, {len(image) / frames / n_atoms:.2f} B/atom")
     table, bx, tm, nf, na = formats._scan_xtc(image)
     padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
     out = np.empty((nf, na, 3), dtype=np.float32)
     t0 = time.perf_counter()
     _lib.check(lib.cgb_xtc_decode_host(_lib.ptr(padded), _lib.ptr(table), nf, na, _lib.ptr(out)))
     t_dec = time.perf_counter() - t0
-    print(f"decode (host, 1 core): {nf * na / t_dec:.3e} atoms/s")
+    print(f"decode (host, all cores): {nf * na / t_dec:.3e} atoms/s")
     pinned = torch.from_numpy(padded).pin_memory()
     table_dev = device.to_device(table, dev)
     img_dev = torch.empty_like(pinned, device=dev)

@@ -477,3 +477,48 @@ def test_s5_size_sampled_terms(options):
             assert (diff <= tol).all(), (bond.atoms, float(diff.max()))
         checked += got.size
     assert checked > 79 * 4 * 4
+
+
+def test_measure_outputs_stay_inside_their_buffers(options):
+    """compute-sanitizer is not available on this GPU pool, so the write bounds of K2 are checked with canaries:
+    `values`, `partials` and `hist` live inside larger sentinel-filled buffers that must come back untouched
+    (odd frame count, several tiles, frame blocks that do not divide the trajectory)."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth
+    sysm = synth.membrane(70, 40, seed=23)
+    n_frames = 37
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    bondset = BondSet(bnd_path, options)
+    bondset.apply(cg)
+    st = bondset._state
+    plan = st.plan
+    n2, n3, n4 = plan.counts
+    n_cols = n2 + n3 + n4
+    assert n_cols > 3 * _lib.MEASURE_TILE
+    dev = st.values.device
+    d = BondSet._device_plan(plan, dev)
+    guard = 4096
+    vbuf = torch.full((n_frames * n_cols + 2 * guard,), -12345.0, dtype=torch.float32, device=dev)
+    pbuf = torch.full((plan.n_bonds * _lib.NPART + 2 * guard,), -7.0, dtype=torch.float64, device=dev)
+    hbuf = torch.full((plan.n_bonds * 128 + 2 * guard,), -3, dtype=torch.int64, device=dev)
+    values = vbuf[guard:guard + n_frames * n_cols]
+    partials = pbuf[guard:guard + plan.n_bonds * _lib.NPART]
+    hist = hbuf[guard:guard + plan.n_bonds * 128]
+    partials.zero_()
+    hist.zero_()
+    lo, hi = torch.from_numpy(st.hist_lo).to(dev), torch.from_numpy(st.hist_hi).to(dev)
+    box_dev = cg._trajectory.device_box_vectors(dev)
+    _lib.check(_lib.load().cgb_measure(
+        device.dptr(cg._trajectory.device_xyz()), device.dptr(box_dev), 1, n_frames, plan.n_beads,
+        device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), device.dptr(d["col_slot"]), plan.max_slots,
+        device.dptr(d["tile_span"]), plan.max_span, n2, n3, n4, plan.n_bonds, device.dptr(st.shift),
+        device.dptr(values), device.dptr(partials), device.dptr(hist), device.dptr(lo), device.dptr(hi), 128,
+        device.stream_handle()))
+    torch.cuda.synchronize()
+    for buf, fill in ((vbuf, -12345.0), (pbuf, -7.0), (hbuf, -3)):
+        assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all())
+    assert torch.equal(values, st.values)                       # and the same results as through the API
+    assert torch.equal(hist.view(plan.n_bonds, 128), st.hist)
+    assert bool((values != -12345.0).all())

@@ -10,7 +10,6 @@ into the device-resident trajectory the mapping kernel reads.
 """
 
 import ctypes
-import struct
 
 import numpy as np
 
@@ -272,7 +271,6 @@ def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, blo
     """``cgb_xtc_decode`` over blocks of frames (one launch handles at most 65535 frames; the
     checkpoint workspace is sized for one block and reused).  Decodes frames [frame0, frame0 + n_frames)
     of the table into ``xyz_dev[0:n_frames]``."""
-    import torch
     from . import device as dev
     lib = _lib.load()
     block = int(min(block, max(n_frames, 1)))

@@ -21,6 +21,13 @@ ANGLE_ABS = 2e-6      # float32 acos / atan2 implementations differ in the last 
 COS_ULPS = 4e-7       # the cosine fed to acos differs by a few float32 ulps (fused vs un-fused dot products)
 
 
+def _acos_tolerance(theta):
+    """Change of acos when its argument moves by COS_ULPS: d(cos) / sin(theta) away from the poles, and at most
+    sqrt(2 d(cos)) next to them (cos = +-(1 - t^2 / 2) at distance t from a pole)."""
+    sin = np.abs(np.sin(np.asarray(theta, dtype=np.float64)))
+    return np.minimum(COS_ULPS / np.maximum(sin, 1e-12), math.sqrt(2 * COS_ULPS))
+
+
 def _assert_values(bond, term, cg=None):
     """Lengths: bit-exact.  Angles / dihedrals: float32 acos / atan2 of quantities that differ by a
     few ulps (fused vs un-fused products), so the tolerance follows the conditioning of the term:
@@ -35,7 +42,7 @@ def _assert_values(bond, term, cg=None):
     diff = np.minimum(diff, 2 * math.pi - diff)
     tol = np.full(diff.shape, ANGLE_ABS)
     if len(term.atoms) == 3:
-        tol = tol + COS_ULPS / np.maximum(np.sin(ref.astype(np.float64)), 1e-3)
+        tol = tol + _acos_tolerance(ref)
     elif cg is not None:
         q = term.indices
         b1 = ogeom.displacement(cg.xyz, q[:, 0], q[:, 1], cg.box_vectors).astype(np.float64)
@@ -379,7 +386,10 @@ def test_degenerate_and_nan_terms_follow_the_reference(options, tmp_path, n_fram
                 regular &= frames_ok != f
             assert (diff[regular] < 2e-4).all(), (bond.atoms, diff.max())
         lo, hi = HIST_RANGES[len(term.atoms)]
-        want, _ = np.histogram(got[~np.isnan(got)].astype(np.float64), bins=HIST_BINS, range=(np.float32(lo), np.float32(hi)))
+        # edges are float64 linspace of the float32 range limits (Python floats: numpy would otherwise round the
+        # edges to float32)
+        want, _ = np.histogram(got[~np.isnan(got)].astype(np.float64), bins=HIST_BINS,
+                               range=(float(np.float32(lo)), float(np.float32(hi))))
         assert np.array_equal(hist[k], want), bond.atoms
         if n_frames >= 13 and not any(a in ("B0", "B1", "B4", "B5", "B6") for a in term.atoms):
             _assert_params(bond, term)
@@ -473,7 +483,7 @@ def test_s5_size_sampled_terms(options):
             assert np.array_equal(got, ref), bond.atoms
         else:
             diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
-            tol = ANGLE_ABS + COS_ULPS / np.maximum(np.sin(ref.astype(np.float64)), 1e-3)
+            tol = ANGLE_ABS + _acos_tolerance(ref)
             assert (diff <= tol).all(), (bond.atoms, float(diff.max()))
         checked += got.size
     assert checked > 79 * 4 * 4

@@ -37,8 +37,8 @@ def check_case(rng, case):
         sysm = synth.membrane(int(rng.integers(1, 60)), int(rng.integers(0, 400)) if kind == "membrane_water" else 0,
                               seed=int(rng.integers(1 << 30)))
     n_frames = int(rng.choice([1, 2, 3, 5, 8, 17, 33, 64, 129, 257]))
-    box_mode = rng.choice(["large", "tight", "none"])
-    if box_mode == "tight":
+    box_mode = rng.choice(["large", "tight", "none", "triclinic"])
+    if box_mode in ("tight", "triclinic"):
         sysm.box = np.array(rng.uniform(2.2, 3.5, 3))
     options = Options()
     # synthetic atom names (A0, A1, ...) carry no element, so masses cannot be guessed: geom / first only
@@ -50,6 +50,10 @@ def check_case(rng, case):
     # device-side slice: frame 0 of the call starts N * 12 bytes into the allocation (not 16-byte aligned in general)
     xyz_dev = torch.from_numpy(full).cuda()[1:]
     box = None if box_mode == "none" else sysm.box_vectors(n_frames, 1)
+    if box_mode == "triclinic":          # mapping keeps using the lengths only; measurement searches 27 images
+        box[:, 1, 0] = rng.uniform(-1.2, 1.2)
+        box[:, 2, 0] = rng.uniform(-1.2, 1.2)
+        box[:, 2, 1] = rng.uniform(-1.2, 1.2)
     map_path, bnd_path = sysm.write_files()
     tune = (int(rng.choice([0, 4096, 8192, 24576])), int(rng.choice([0, 2, 3])), int(rng.choice([0, 16, 128])))
     lib.cgb_map_set_tuning(*tune)
@@ -98,7 +102,8 @@ def check_case(rng, case):
                         q = term.indices[w % len(term.indices)]
                         f = w // len(term.indices)
                         x = ocg.xyz[f].astype(np.float64)
-                        bx = None if ocg.box_vectors is None else np.diag(ocg.box_vectors[f]).astype(np.float64)
+                        bx = None if ocg.box_vectors is None or box_mode == "triclinic" else \
+                            np.diag(ocg.box_vectors[f]).astype(np.float64)
                         def mic(d):
                             return d if bx is None else d - bx * np.round(d / bx)
                         if len(q) == 3:

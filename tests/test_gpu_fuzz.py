@@ -20,4 +20,4 @@ def test_random_cases_against_the_oracle():
     for case in range(60):
         kind, n_frames, box_mode, n_terms = fuzz.check_case(rng, case)      # raises AssertionError on a mismatch
         kinds.add((str(kind), str(box_mode)))
-    assert len(kinds) >= 6          # the draw covered membranes, solvated membranes and chains, with and without box
+    assert len(kinds) >= 8          # membranes, solvated membranes and chains x large / tight / triclinic / no box

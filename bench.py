@@ -27,6 +27,7 @@ Multi-GPU (torchrun, one rank per GPU): frames are independent, so every rank ma
 
 import argparse
 import json
+import math
 import os
 import pathlib
 import statistics
@@ -534,6 +535,27 @@ def run_b200(args):
                 line["ingest"] = ingest_leg(sysm, mapper, plan, dev)
             except Exception as exc:
                 line["ingest"] = {"error": repr(exc)}
+    if world > 1 and not args.no_extras:
+        # bond-measures/s at N GPUs (weak scaling): every rank measures its own 1,048,576-frame S3 shard; the
+        # shift broadcast and the all-reduce of the partial moments / histograms (NCCL) run inside BondSet
+        del xyz, out
+        torch.cuda.empty_cache()
+        leg, ms = None, float("inf")
+        try:
+            leg = measure_leg(dev, peak_gbs)
+            ms = leg["ms_per_pass"]
+        except Exception as exc:  # noqa: BLE001 -- keep the ranks in step: the reduction below still runs
+            leg = {"error": repr(exc)}
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        if "error" not in leg and math.isfinite(float(t.item())):
+            per_rank = leg["value"] * leg["ms_per_pass"] * 1e-3
+            leg["ms_per_pass"] = float(t.item())
+            leg["value"] = world * per_rank / (leg["ms_per_pass"] * 1e-3)
+            leg["scaling"] = "weak: one 1,048,576-frame shard per rank, max time over ranks"
+            for key in ("achieved_gbs", "frac_of_hbm_peak", "algorithmic_bytes"):
+                leg.pop(key, None)
+        line["measure"] = leg
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -532,3 +532,58 @@ def test_measure_outputs_stay_inside_their_buffers(options):
     assert torch.equal(values, st.values)                       # and the same results as through the API
     assert torch.equal(hist.view(plan.n_bonds, 128), st.hist)
     assert bool((values != -12345.0).all())
+
+
+def test_gather_kernels_explicit_and_automatic(options, tmp_path):
+    """The gather kernels (beads read from global memory) are the path for tiles whose bead range does not fit
+    in shared memory.  (1) forced through `BondSet.staged = False` on a membrane; (2) reached automatically by a
+    4,000-bead chain with terms that join its two ends (one frame of the tile's range is 48 KB)."""
+    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    sysm = synth.membrane(30, 20, seed=31)
+    sysm.box = np.array([3.6, 3.3, 3.9])
+    n_frames = 19
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    ocg = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, xyz, box))
+    terms = obonds.parse_bnd(bnd_path, generate_angles=options.generate_angles,
+                             generate_dihedrals=options.generate_dihedrals)
+    obonds.measure(terms, ocg)
+    obonds.invert(terms)
+    staged, gather = BondSet(bnd_path, options), BondSet(bnd_path, options)
+    gather.staged = False
+    for bondset in (staged, gather):
+        bondset.apply(cg)
+        bondset.boltzmann_invert()
+    for mol in terms:
+        for a, b, term in zip(staged[mol], gather[mol], terms[mol]):
+            _assert_values(b, term, ocg)
+            _assert_params(b, term)
+            if len(term.atoms) == 2:
+                assert np.array_equal(np.asarray(a.values), np.asarray(b.values))
+
+    # (2) a chain whose first and last beads are bonded: the tile spans the whole 4,000-bead frame
+    n_beads = 4000
+    rng = np.random.default_rng(9)
+    xyz = (np.cumsum(rng.normal(0, 0.2, (1, n_beads, 3)), axis=1) + rng.normal(0, 0.05, (7, n_beads, 3))).astype(np.float32)
+    names = [f"B{i}" for i in range(n_beads)]
+    from pycgtool_b200.topology import Topology
+    top = Topology.from_residue_lists([("MOL", names)])
+    box = np.zeros((7, 3, 3), dtype=np.float32)
+    box[:, 0, 0] = box[:, 1, 1] = box[:, 2, 2] = 9.0
+    lines = ["[ MOL ]"] + [f"B{i} B{i + 1}" for i in range(0, n_beads - 1, 7)] + ["B0 B3999", "B1 B3998"]
+    lines += ["B0 B2000 B3999", "B5 B6 B7"] + ["B0 B1 B3998 B3999", "B10 B11 B12 B13"]
+    bnd = tmp_path / "long.bnd"
+    bnd.write_text("\n".join(lines) + "\n")
+    frame = Frame.from_arrays(top, xyz, unitcell_vectors=box)
+    bondset = BondSet(bnd, options)
+    bondset.apply(frame)
+    bondset.boltzmann_invert()
+    assert bondset._state.plan.max_span >= 3999
+    terms = obonds.parse_bnd(bnd, generate_angles=False, generate_dihedrals=False)
+    osys = oracle_system(top, xyz, box)
+    obonds.measure(terms, osys)
+    obonds.invert(terms)
+    for bond, term in zip(bondset["MOL"], terms["MOL"]):
+        _assert_values(bond, term, osys)
+        _assert_params(bond, term)

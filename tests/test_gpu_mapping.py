@@ -303,3 +303,28 @@ def test_s5_size_sampled_beads(options):
         atom_xyz = np.ascontiguousarray(coords[:, sel].transpose(1, 0, 2))          # (atoms, frames, 3)
         ref = omap.calc_coords_weight(atom_xyz[0], atom_xyz, plan.weights[lo:hi], lengths)
         assert np.array_equal(out[:, k], ref.astype(np.float32)), int(b)
+
+
+@pytest.mark.parametrize("n_frames", [1, 6, 37])
+def test_float64_weights_on_many_tiles(options, n_frames):
+    """ITP masses make the bead weights float64 (mapping.py:224-227) and the bead sum a float64 sum rounded to
+    float32 at the end: random float64 weights on a solvated membrane (hundreds of tiles), bit-exact vs the oracle."""
+    from pycgtool_b200 import Frame, Mapping, synth
+    sysm = synth.membrane(12, 150, seed=77)
+    sysm.box = np.array([3.3, 3.0, 3.4])
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    map_path, _ = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    mols = omap.parse_map(map_path)
+    rng = np.random.default_rng(3)
+    for mol in mols:
+        for bead, obead in zip(mapper[mol], mols[mol]):
+            w = rng.uniform(0.5, 16.0, len(bead.atoms))
+            w = w / w.sum()                         # float64, like masses / total mass
+            bead.weights = w
+            obead.weights = w.copy()
+    cg = mapper.apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    ref = omap.apply(mols, oracle_system(sysm.topology, xyz, box))
+    got = cg._trajectory.xyz
+    assert got.dtype == np.float32 and got.shape == ref.xyz.shape
+    assert np.array_equal(got, ref.xyz.astype(np.float32))

@@ -328,3 +328,29 @@ def test_float64_weights_on_many_tiles(options, n_frames):
     got = cg._trajectory.xyz
     assert got.dtype == np.float32 and got.shape == ref.xyz.shape
     assert np.array_equal(got, ref.xyz.astype(np.float32))
+
+
+def test_virtual_beads_on_a_membrane(options, tmp_path):
+    """Virtual sites (``@v`` lines: built from CG beads of the same residue after the real beads,
+    mapping.py:431-438) on every lipid of a membrane whose molecules straddle the box: bit-exact vs the oracle,
+    real beads through the tile kernel, virtual beads through the gather kernel reading the CG frame."""
+    from pycgtool_b200 import Frame, Mapping, synth
+    sysm = synth.membrane(25, 30, seed=41)
+    sysm.box = np.array([3.1, 3.4, 2.8])
+    text = sysm.map_text.replace("[ POPC ]", "@v VHD P1 NC3 PO4 GL1 GL2\n@v VTA C1 C1A C2A C3A C4A\n[ POPC ]", 1)
+    # the POPC section gets one as well (appended at its end = before the next section or the end of the file)
+    head, _, tail = text.partition("[ POPC ]")
+    nxt = tail.find("\n[")
+    tail = tail + "@v VMID P1 GL1 GL2 C1A C1B\n" if nxt < 0 else tail[:nxt + 1] + "@v VMID P1 GL1 GL2 C1A C1B\n" + tail[nxt + 1:]
+    map_path = tmp_path / "virtual.map"
+    map_path.write_text(head + "[ POPC ]" + tail)
+    n_frames = 23
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    mapper = Mapping(map_path, options)
+    cg = mapper.apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    ref = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, xyz, box))
+    got = cg._trajectory.xyz
+    assert got.shape == ref.xyz.shape and got.shape[1] > sysm.topology.n_residues
+    names = [a.name for a in cg.residue(0).atoms]
+    assert "VHD" in names and "VTA" in names
+    assert np.array_equal(got, ref.xyz)

@@ -99,6 +99,21 @@ int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_frames, int6
                   const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries, const double* entries_w64,
                   int32_t max_span, int32_t max_tile_entries, float* cg_xyz, void* stream);
 
+/* K1 over an atom window: xyz holds only atoms [first_atom, first_atom + n_atoms) of every frame
+ * ([F][n_atoms][3]); the tile plan keeps its absolute atom numbers and must not reference atoms outside the
+ * window.  With first_atom = 0 this is cgb_map_tiles.  Used when a host trajectory is streamed: unmapped
+ * solvent never crosses PCIe. */
+int cgb_map_tiles_window(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms, int64_t first_atom,
+                         int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries,
+                         const double* entries_w64, int32_t max_span, int32_t max_tile_entries, float* cg_xyz,
+                         void* stream);
+
+/* Host -> device copy of the atom window [first_atom, first_atom + n_window_atoms) of n_frames frames of a host
+ * trajectory [F][n_atoms][3] (page-locked for an asynchronous copy) into a dense device buffer
+ * [F][n_window_atoms][3]: one strided copy (cudaMemcpy2DAsync) on `stream`. */
+int cgb_copy_window_h2d(float* dst, const float* src, int64_t n_frames, int64_t n_atoms, int64_t first_atom,
+                        int64_t n_window_atoms, void* stream);
+
 /* K1g: gather kernel over a CSR list, used for virtual beads (src = cg_xyz, mapping.py:431-438) and as
  * the path for beads too wide for a tile.  bead_list: device int32[n_list] of output beads to compute. */
 int cgb_map_gather(const float* src, int64_t src_atoms, const float* box_len, int64_t n_frames, int64_t n_beads,

@@ -50,6 +50,8 @@ SIGNATURES = {
     "cgb_map_plan_size": (_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cgb_map_plan_build": (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cgb_map_tiles": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "cgb_map_tiles_window": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "cgb_copy_window_h2d": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "cgb_map_set_tuning": (_int, [_i32, _i32, _i32]),
     "cgb_map_set_shape": (_int, [_i32, _i32]),

@@ -178,6 +178,7 @@ struct MapParams {
     const float* xyz;
     const float* box;  // [F][3] or nullptr
     int64_t F, N, B;
+    int64_t base;      // first atom held by xyz: the buffer is the window [base, base + N) of every frame
     const CgbMapTile* tiles;
     const CgbMapEntry* ent;
     const double* w64;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
             const float* src = nullptr;
             if (lane < ncopies) {
                 src = p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
-                                   : p.xyz + ((size_t)(f0 + lane) * p.N + tile.atom0) * 3;
+                                   : p.xyz + ((size_t)(f0 + lane) * p.N + (size_t)(tile.atom0 - p.base)) * 3;
                 bytes = span_bytes(src, nfl, lo, hi, &edge);
             }
             // runs touching the first / last bytes of the whole array are copied by hand
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(kProducerThreads + 256) map_tiles_kernel(const
         // byte misalignment of the first frame's tile (of the whole stage in contiguous mode)
         const uint32_t h0b = (uint32_t)(reinterpret_cast<uintptr_t>(
                                  p.contiguous ? p.xyz + (size_t)f0 * p.N * 3
-                                              : p.xyz + ((size_t)f0 * p.N + tile.atom0) * 3) & 15u);
+                                              : p.xyz + ((size_t)f0 * p.N + (size_t)(tile.atom0 - p.base)) * 3) & 15u);
         mbar_wait(&full[s], (it / p.nstage) & 1);
         if (resident) {
             if (warp < nchunks)
@@ -611,8 +612,28 @@ extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_f
                              int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries,
                              const double* entries_w64, int32_t max_span, int32_t max_tile_entries, float* cg_xyz,
                              void* stream) {
+    return cgb_map_tiles_window(xyz, box_len, n_frames, n_atoms, 0, n_beads, tiles, n_tiles, entries, entries_w64,
+                                max_span, max_tile_entries, cg_xyz, stream);
+}
+
+extern "C" int cgb_copy_window_h2d(float* dst, const float* src, int64_t n_frames, int64_t n_atoms, int64_t first_atom,
+                                   int64_t n_window_atoms, void* stream) {
+    if (n_frames < 0 || n_atoms < 0 || first_atom < 0 || n_window_atoms < 0 || first_atom + n_window_atoms > n_atoms)
+        return CGB_EINVAL;
+    if (n_frames == 0 || n_window_atoms == 0) return CGB_OK;
+    if (!dst || !src) return CGB_EINVAL;
+    return (int)cudaMemcpy2DAsync(dst, (size_t)n_window_atoms * 12, src + (size_t)first_atom * 3, (size_t)n_atoms * 12,
+                                  (size_t)n_window_atoms * 12, (size_t)n_frames, cudaMemcpyHostToDevice,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cgb_map_tiles_window(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms,
+                                    int64_t first_atom, int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles,
+                                    const CgbMapEntry* entries, const double* entries_w64, int32_t max_span,
+                                    int32_t max_tile_entries, float* cg_xyz, void* stream) {
     using namespace cgb;
-    if (n_frames < 0 || n_atoms < 0 || n_beads < 0 || n_tiles < 0 || max_span < 0 || max_tile_entries < 0)
+    if (n_frames < 0 || n_atoms < 0 || n_beads < 0 || n_tiles < 0 || max_span < 0 || max_tile_entries < 0 ||
+        first_atom < 0)
         return CGB_EINVAL;
     if (n_frames == 0 || n_tiles == 0) return CGB_OK;
     if (!xyz || !tiles || !entries || !cg_xyz) return CGB_EINVAL;
@@ -624,6 +645,7 @@ extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_f
     p.box = box_len;
     p.F = n_frames;
     p.N = n_atoms;
+    p.base = first_atom;
     p.B = n_beads;
     p.tiles = tiles;
     p.ent = entries;
@@ -636,7 +658,7 @@ extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_f
     // A single tile in a frame no larger than a slot: stage whole frames, one bulk copy per stage.
     // Small stages keep many CTAs resident (the sweep under profiles/ favours ~12 KB there).
     const int64_t frame_bytes = n_atoms * 12;
-    p.contiguous = (n_tiles == 1 && frame_bytes * fg <= g_stage_bytes) ? 1 : 0;
+    p.contiguous = (n_tiles == 1 && first_atom == 0 && frame_bytes * fg <= g_stage_bytes) ? 1 : 0;
     if (p.contiguous) {
         const int64_t budget = g_stage_user ? g_stage_bytes : g_stage_bytes / 2;
         int k = (int)std::max<int64_t>(fg, budget / std::max<int64_t>(frame_bytes, 1));

@@ -454,17 +454,20 @@ class Mapping:
         return d
 
     # ------------------------------------------------------------------ apply (mapping.py:391-443)
-    def map_device(self, plan, xyz_dev, box_lengths, out=None):
+    def map_device(self, plan, xyz_dev, box_lengths, out=None, window=None):
         """Run the mapping kernels on device-resident coordinates.
 
         ``xyz_dev``: CUDA float32 tensor (F, N, 3); ``box_lengths``: numpy / tensor
         (F, 3) or None.  Returns the CUDA tensor (F, B, 3).  Asynchronous.
+        ``window=(first_atom, n_atoms)``: ``xyz_dev`` holds only that atom range of every frame
+        (``atom_window``), as uploaded by ``map_streamed``.
         """
         import torch
         lib = _lib.load()
         dev = xyz_dev.device
         n_frames = int(xyz_dev.shape[0])
-        if xyz_dev.dtype != torch.float32 or not xyz_dev.is_contiguous() or int(xyz_dev.shape[1]) != plan.n_atoms:
+        first_atom, held = (0, plan.n_atoms) if window is None else (int(window[0]), int(window[1]))
+        if xyz_dev.dtype != torch.float32 or not xyz_dev.is_contiguous() or int(xyz_dev.shape[1]) != held:
             raise ValueError("xyz must be a contiguous float32 (F, N, 3) tensor matching the topology")
         if out is None:
             out = torch.empty((n_frames, plan.n_beads, 3), dtype=torch.float32, device=dev)
@@ -476,11 +479,14 @@ class Mapping:
             box_dev = device.to_device(box_lengths, dev, dtype=np.float32) if not isinstance(
                 box_lengths, torch.Tensor) else box_lengths.to(dev).contiguous()
         stream = device.stream_handle()
+        if window is not None and d["n_wide"]:
+            raise ValueError("an atom window cannot be combined with beads wider than a tile")
         if d["n_tiles"]:
-            _lib.check(lib.cgb_map_tiles(device.dptr(xyz_dev), device.dptr(box_dev), n_frames, plan.n_atoms,
-                                         plan.n_beads, device.dptr(d["tiles"]), d["n_tiles"],
-                                         device.dptr(d["entries"]), device.dptr(d["entries_w64"]),
-                                         d["max_span"], d["max_ent"], device.dptr(out), stream), "cgb_map_tiles")
+            _lib.check(lib.cgb_map_tiles_window(device.dptr(xyz_dev), device.dptr(box_dev), n_frames, held, first_atom,
+                                                plan.n_beads, device.dptr(d["tiles"]), d["n_tiles"],
+                                                device.dptr(d["entries"]), device.dptr(d["entries_w64"]),
+                                                d["max_span"], d["max_ent"], device.dptr(out), stream),
+                       "cgb_map_tiles_window")
         if d["n_wide"]:
             _lib.check(lib.cgb_map_gather(device.dptr(xyz_dev), plan.n_atoms, device.dptr(box_dev), n_frames,
                                           plan.n_beads, device.dptr(d["bead_ptr"]), device.dptr(d["index"]),
@@ -495,6 +501,17 @@ class Mapping:
                        "cgb_map_gather")
         return out
 
+    @staticmethod
+    def atom_window(plan):
+        """``(first_atom, n_atoms)``: the contiguous range of input atoms the real beads are built from.  When a
+        host trajectory is streamed only this range is uploaded -- unmapped solvent after (or before) the mapped
+        molecules never crosses PCIe."""
+        if getattr(plan, "_atom_window", None) is None:
+            real_entry = np.repeat(plan.is_virtual == 0, np.diff(plan.bead_ptr))
+            atoms = plan.index[real_entry]
+            plan._atom_window = (0, plan.n_atoms) if len(atoms) == 0 else (int(atoms.min()), int(atoms.max()) + 1 - int(atoms.min()))
+        return plan._atom_window
+
     def map_streamed(self, plan, xyz_host, box_lengths, chunk_bytes=256 << 20, out_host=None):
         """Map a host-resident trajectory through a double-buffered H2D -> kernel -> D2H pipeline.
 
@@ -507,12 +524,19 @@ class Mapping:
         dev = device.default_device()
         n_frames, n_atoms = int(xyz_host.shape[0]), plan.n_atoms
         src = torch.from_numpy(xyz_host)
-        chunk = int(max(1, min(n_frames, chunk_bytes // max(12 * n_atoms, 1))))
+        lib = _lib.load()
+        # upload only the atoms the mapping reads when that saves at least a tenth of the transfer
+        first_atom, held = self.atom_window(plan)
+        windowed = (held <= 0.9 * n_atoms and held * 12 > (64 << 10) and not self._device_plan(plan, dev)["n_wide"]
+                    and src.is_contiguous())
+        if not windowed:
+            first_atom, held = 0, n_atoms
+        chunk = int(max(1, min(n_frames, chunk_bytes // max(12 * held, 1))))
         cg_dev = torch.empty((n_frames, plan.n_beads, 3), dtype=torch.float32, device=dev)
         if out_host is None:
             out_host = torch.empty((n_frames, plan.n_beads, 3), dtype=torch.float32, pin_memory=True)
         box_dev = None if box_lengths is None else device.to_device(box_lengths, dev, dtype=np.float32)
-        bufs = [torch.empty((chunk, n_atoms, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        bufs = [torch.empty((chunk, held, 3), dtype=torch.float32, device=dev) for _ in range(2)]
         main = torch.cuda.current_stream()
         h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
         h2d.wait_stream(main)
@@ -524,11 +548,15 @@ class Mapping:
             with torch.cuda.stream(h2d):
                 if mapped[slot] is not None:
                     h2d.wait_event(mapped[slot])
-                bufs[slot][:f1 - f0].copy_(src[f0:f1], non_blocking=True)
+                if windowed:
+                    _lib.check(lib.cgb_copy_window_h2d(device.dptr(bufs[slot]), src[f0:f1].data_ptr(), f1 - f0, n_atoms,
+                                                       first_atom, held, h2d.cuda_stream), "cgb_copy_window_h2d")
+                else:
+                    bufs[slot][:f1 - f0].copy_(src[f0:f1], non_blocking=True)
                 loaded = h2d.record_event()
             main.wait_event(loaded)
             self.map_device(plan, bufs[slot][:f1 - f0], None if box_dev is None else box_dev[f0:f1],
-                            out=cg_dev[f0:f1])
+                            out=cg_dev[f0:f1], window=(first_atom, held) if windowed else None)
             mapped[slot] = main.record_event()
             with torch.cuda.stream(d2h):
                 d2h.wait_event(mapped[slot])

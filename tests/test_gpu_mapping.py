@@ -354,3 +354,50 @@ def test_virtual_beads_on_a_membrane(options, tmp_path):
     names = [a.name for a in cg.residue(0).atoms]
     assert "VHD" in names and "VTA" in names
     assert np.array_equal(got, ref.xyz)
+
+
+@pytest.mark.parametrize("solvent_first", [False, True])
+def test_streamed_host_trajectory_uploads_only_the_mapped_atom_window(options, monkeypatch, solvent_first):
+    """A host-resident trajectory whose solvent is not mapped: the streamed path uploads only the atom range the
+    beads are built from (strided H2D copy + the windowed kernel entry) and gives the floats of the oracle and of the
+    device-resident path.  Solvent before the lipids exercises a non-zero first atom (and unaligned window rows)."""
+    import torch
+    import pycgtool_b200.mapping as pm
+    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200.topology import Topology
+    sysm = synth.membrane(25, 2501, seed=13)
+    sysm.box = np.array([4.0, 4.1, 3.7])
+    n_frames = 21
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    top = sysm.topology
+    if solvent_first:
+        # move the W4 residues in front of the lipids (same coordinates, permuted)
+        res = [(top.res_names[top.res_name_id[r]], [top.atom_names[i] for i in
+                top.atom_name_id[top.res_first[r]:top.res_first[r + 1]]]) for r in range(top.n_residues)]
+        order = [r for r, (name, _) in enumerate(res) if name == "W4"] + [r for r, (name, _) in enumerate(res) if name != "W4"]
+        atoms = np.concatenate([np.arange(top.res_first[r], top.res_first[r + 1]) for r in order])
+        top = Topology.from_residue_lists([res[r] for r in order])
+        xyz = np.ascontiguousarray(xyz[:, atoms])
+    map_path, _ = sysm.write_files()
+    map_path.write_text(map_path.read_text().replace("[ W4 ]", "[ NOTW4 ]"))      # the solvent is not mapped
+    mapper = Mapping(map_path, options)
+    plan = mapper._plan_for(top)
+    first, held = Mapping.atom_window(plan)
+    assert held == 25 * (138 + 134) and first == (2501 * 12 if solvent_first else 0)
+    calls = []
+    lib = pm._lib.load()
+    real = lib.cgb_copy_window_h2d
+
+    def spy(*args):
+        calls.append(args[2:6])
+        return real(*args)
+
+    monkeypatch.setattr(lib, "cgb_copy_window_h2d", spy, raising=False)
+    monkeypatch.setattr(pm, "STREAM_THRESHOLD_BYTES", 0)
+    pinned = torch.from_numpy(xyz).pin_memory()
+    streamed = mapper.apply(Frame.from_arrays(top, pinned.numpy(), unitcell_vectors=box))._trajectory.xyz
+    assert calls and all(c[1] == top.n_atoms and c[2] == first and c[3] == held for c in calls)
+    resident = mapper.apply(Frame.from_arrays(top, unitcell_vectors=box, xyz_device=torch.from_numpy(xyz).cuda()))
+    ref = omap.apply(omap.parse_map(map_path), oracle_system(top, xyz, box))
+    assert np.array_equal(streamed, ref.xyz)
+    assert np.array_equal(resident._trajectory.xyz, ref.xyz)

@@ -146,7 +146,7 @@ class MeasurePlan:
         self.counts = (0, 0, 0)       # columns per kind (lengths, angles, dihedrals)
         self.col_beads = None         # int32 (M, 4)
         self.col_bond = None          # int32 (M,)
-        self.col_slot = None          # int32 (M,) compact Bond number inside each 256-column tile of a kind
+        self.col_slot = None          # int32 (M,) compact Bond number inside each tile of _lib.MEASURE_TILE columns of a kind
         self.max_slots = 0
         self.tile_span = None         # int32 (T, 2): (first bead, beads) of the range each tile gathers from
         self.max_span = 0

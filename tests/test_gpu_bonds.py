@@ -587,3 +587,24 @@ def test_gather_kernels_explicit_and_automatic(options, tmp_path):
     for bond, term in zip(bondset["MOL"], terms["MOL"]):
         _assert_values(bond, term, osys)
         _assert_params(bond, term)
+
+
+def test_statistics_are_reproducible_run_to_run(options):
+    """No floating-point atomics inside a CTA (fixed-order float64 reduction); CTAs are combined with float64
+    atomics, whose order can only move the last bits: repeated passes agree to 1e-13, histograms exactly."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    sysm = synth.small_molecule()
+    n_frames = 1 << 16
+    xyz = sysm.coordinates_device(n_frames, torch.device("cuda"), chunk=1 << 14)
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(
+        Frame.from_arrays(sysm.topology, unitcell_vectors=sysm.box_vectors(n_frames), xyz_device=xyz))
+    runs = []
+    for _ in range(3):
+        bondset = BondSet(bnd_path, options)
+        bondset.apply(cg)
+        runs.append((bondset._state.partials.cpu().numpy().copy(), bondset._state.hist.cpu().numpy().copy()))
+    for partials, hist in runs[1:]:
+        assert np.array_equal(hist, runs[0][1])
+        np.testing.assert_allclose(partials, runs[0][0], rtol=1e-13, atol=1e-13)

@@ -124,7 +124,7 @@ class ClockSampler:
 # workloads
 # --------------------------------------------------------------------------------------------
 def make_system(name):
-    from pycgtool_b200 import synth
+    from workloads import synth
     if name == "s2":
         return synth.s2(), S2_FRAMES, "S2 map-only DOPC/POPC membrane: 1,152 lipids, N=156,672 atoms -> 13,824 beads, 10,000 frames"
     if name == "s4":
@@ -224,8 +224,9 @@ def measure_leg(dev, peak_gbs, workload="s3"):
     circular sums + 128-bin histograms); `api_ms_per_pass` is `BondSet.apply` as a user calls it
     (adds buffer allocation and the one-frame shift pre-pass)."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth
-    from pycgtool_b200.synth import Options
+    from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device
+    from workloads import synth
+    from workloads.synth import Options
     lib = _lib.load()
     if workload == "s3":
         sysm, n_frames, chunk = synth.small_molecule(), 1 << 20, 1 << 16
@@ -391,7 +392,7 @@ def run_b200(args):
             os.close(saved)
 
     from pycgtool_b200 import Frame, Mapping, _lib
-    from pycgtool_b200.synth import Options
+    from workloads.synth import Options
     lib = _lib.load()            # fails loudly if the CUDA library is missing
 
     peak_gbs, peak_src = load_peaks()

@@ -14,8 +14,8 @@
  *   - plain pointers and sizes only; no C++ or torch types cross the boundary;
  *   - "device" pointers are CUDA device memory owned by the caller; "host" pointers are ordinary memory;
  *   - every launch is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream)
- *     and returns without synchronising; the library allocates nothing and keeps no state besides the
- *     process-wide benchmarking knobs (cgb_map_set_tuning / cgb_map_set_shape / cgb_measure_set_tuning);
+ *     and returns without synchronising; the library allocates nothing and keeps no mutable state (tuning
+ *     knobs are per-call arguments), so calls are re-entrant across streams and threads;
  *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative CGB_E* on bad arguments;
  *   - all index tables are int32; frames, atoms and beads are counted in int64.
  */
@@ -28,14 +28,15 @@
 extern "C" {
 #endif
 
-#define CGB_ABI_VERSION 1
+#define CGB_ABI_VERSION 2
 
 enum {
     CGB_OK = 0,
     CGB_EINVAL = -1,      /* NULL pointer, negative size, inconsistent table */
     CGB_ERANGE = -2,      /* index outside the atom / bead range */
     CGB_ETOOBIG = -3,     /* a single bead spans more atoms than a shared-memory tile can hold */
-    CGB_EALIGN = -4       /* pointer not aligned to its element type */
+    CGB_EALIGN = -4,      /* pointer not aligned to its element type */
+    CGB_ENCCL = -5        /* libnccl could not be loaded, or an NCCL call failed */
 };
 
 /* Human-readable text for any return code of this library (CUDA codes included). */
@@ -120,22 +121,29 @@ int cgb_map_gather(const float* src, int64_t src_atoms, const float* box_len, in
                    const int32_t* bead_ptr, const int32_t* index, const void* weights, int weights_f64,
                    const int32_t* bead_list, int64_t n_list, float* cg_xyz, void* stream);
 
-/* Tunables of K1 (0 keeps the built-in default): frames per pipeline stage byte budget, pipeline
- * depth, frames per CTA.  Intended for benchmarking; not needed for correctness. */
-int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta);
-/* More K1 benchmarking knobs: consumer threads per CTA (multiple of 32, <= 256) and frames per register
- * group (1, 2 or 4); 0 keeps the default. */
-int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
+/* Tunables of K1, passed per call (NULL or a zero field keeps the built-in default).  Intended for benchmarking;
+ * not needed for correctness.  The library keeps no mutable global state. */
+typedef struct CgbMapTuning {
+    int32_t stage_bytes;       /* byte budget of one pipeline stage                      */
+    int32_t n_stages;          /* pipeline depth (2..4)                                  */
+    int32_t frames_per_cta;    /* frames one CTA works through                           */
+    int32_t consumer_threads;  /* consumer threads per CTA (multiple of 32, <= 256)      */
+    int32_t frame_group;       /* frames per register group (1, 2 or 4)                  */
+    int32_t reserved[3];
+} CgbMapTuning;
+
+/* K1 with explicit tuning and atom window (cgb_map_tiles / cgb_map_tiles_window call this with tuning = NULL). */
+int cgb_map_tiles_ex(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms, int64_t first_atom,
+                     int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries,
+                     const double* entries_w64, int32_t max_span, int32_t max_tile_entries, float* cg_xyz,
+                     const CgbMapTuning* tuning, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2: bonded-term measurement with streaming statistics.
  *
- * A "column" is one instance of one bonded term (bondset.py:509-528); columns are ordered lengths,
- * then angles, then dihedrals (n2, n3, n4 of them).  col_beads: device int32 [M][4] bead indices
- * (unused trailing entries repeat the last bead); col_bond: device int32 [M] owning Bond.
- * values: device float32, F*M floats stored as one plane per kind, planes in kind order: the plane of a
- * kind with n columns starting at column c0 begins at float F*c0 and is [F][n] frame-major
- * (Bond.values = plane[:, columns of the bond].flatten()); each kernel then writes one contiguous region.
+ * A "column" is one instance of one bonded term (bondset.py:509-528); the caller numbers its columns lengths,
+ * then angles, then dihedrals (n2, n3, n4 of them).  col_beads: int32 [M][4] bead indices (unused trailing
+ * entries repeat the last bead); col_bond: int32 [M] owning Bond.
  *   length   |mic(x1 - x0)|                                         (mdtraj compute_distances)
  *   angle    acos(u.v / |u||v|), u = mic(x0 - x1), v = mic(x2 - x1)  (mdtraj compute_angles)
  *   dihedral atan2((b1.c1)|b2|, c1.c2), b_i = mic(x_i - x_{i-1}), c1 = b2 x b3, c2 = b1 x b2
@@ -143,46 +151,119 @@ int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group);
  * box_vec: device float32 [F][9] rows a,b,c, or NULL (no unit cell).  ortho != 0 selects the
  * orthorhombic minimum image (box diagonal), else the triclinic one (reduce, subtract, 27 images).
  *
+ * values: device float32 [F][row_stride] row-major, or NULL (statistics only: nothing is stored per
+ * measure); Bond.values = values[:, columns of the bond].flatten().  The fused kernel places every column
+ * at the position the plan compiler chose (col_out); the gather entry writes its column j at position j
+ * of the pointer it is given.
+ *
  * partials: device float64 [n_bonds][CGB_NPART], ACCUMULATED into (caller zeroes it once; per-GPU
  * shards are summed with an allreduce):
- *   [0] count of finite values        [1] sum (v - shift)       [2] sum (v - shift)^2
+ *   [0] count of finite values        [1] sum d                 [2] sum d^2
  *   [3] sum cos v                     [4] sum sin v             [5] sum wrap(v - circular mean)^2 (pass 2)
  *   [6] count of all values           [7] reserved
- * shift: device float32 [n_bonds] or NULL (0) -- any value near the data, identical on all shards.
- * hist: device uint64 [n_bonds][n_bins] accumulated, or NULL; bin edges are
+ *   with d = v - shift for lengths and angles, and d = wrap(v - shift) into [-pi, pi] for dihedrals.
+ * shift: device float32 [n_bonds] or NULL (0) -- a value near the data, identical on all shards
+ * (cgb_measure_shift).  The statistics are accumulated in float32 over short runs, so their accuracy
+ * relies on |d| being of the order of the spread of the data.
+ * hist: device float64 [n_bonds][n_bins] integer-valued counts, accumulated, or NULL; bin edges are
  * linspace(hist_lo[b], hist_hi[b], n_bins + 1) with numpy.histogram's edge rules (1 <= n_bins <= 512).
+ * Counts are float64 so that partials and histograms form ONE float64 buffer for the cross-GPU sum.
  * ---------------------------------------------------------------------------------------------- */
 #define CGB_NPART 8
-/* col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one
+
+/* ---- fused kernel (K2): plan ---- */
+#define CGB_MEAS_WARPS 7          /* consumer warps per CTA = groups per tile at most                    */
+#define CGB_MEAS_CHUNKS 4         /* 32-lane chunks per group                                            */
+#define CGB_MEAS_EDGE_CHUNKS 2    /* of which at most this many hold edges (bead pairs)                  */
+
+typedef struct CgbMeasTile {      /* 32 bytes: the work of one CTA */
+    int32_t bead0, span;          /* contiguous bead range staged per frame                              */
+    int32_t group0, ngroups;      /* its groups                                                          */
+    int32_t slot0, nslots;        /* tile_bonds[slot0 .. slot0 + nslots): Bond of every tile-local slot  */
+    int32_t reserved[2];
+} CgbMeasTile;
+
+typedef struct CgbMeasGroup {     /* 32 bytes: the work of one warp */
+    uint8_t kind[CGB_MEAS_CHUNKS];    /* 0 unused, 2 edges, 3 angles, 4 dihedrals; edge chunks come first */
+    uint8_t nlanes[CGB_MEAS_CHUNKS];  /* active lanes of the chunk                                        */
+    uint8_t nemit[CGB_MEAS_CHUNKS];   /* its first nemit lanes produce a column                           */
+    int32_t vcol0[CGB_MEAS_CHUNKS];   /* position in the values row of lane 0's column                    */
+    int32_t reserved;
+} CgbMeasGroup;
+
+/* One lane of a chunk (8 bytes).  Edge lane: ref = a | b << 16, beads relative to the tile's bead0; its record
+ * holds the minimum image of x_b - x_a.  Angle lane: ref = e_u | s_u << 7 | e_v << 8 | s_v << 15, the records
+ * (0..63, numbered through the edge chunks) of u = x0 - x1 and v = x2 - x1, s = 1 when the record is reversed.
+ * Dihedral lane: three such bytes for b1, b2, b3.  slot: tile-local Bond slot, -1 for an edge without a column. */
+typedef struct CgbMeasLane {
+    uint32_t ref;
+    int32_t slot;
+} CgbMeasLane;
+
+typedef struct CgbMeasPlanInfo {
+    int64_t n_tiles, n_groups, n_tile_bonds;
+    int64_t n_wide;               /* columns whose beads are too far apart for a tile (gather kernel)     */
+    int64_t n_staged;             /* columns of the fused kernel: positions [0, n_staged) of the values row */
+    int32_t max_span, max_slots, max_edge_chunks, max_tile_groups;
+} CgbMeasPlanInfo;
+
+/* Limits to compile a plan with, for a histogram of n_bins bins (with_hist = 0: no histogram). */
+int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t* max_span, int32_t* max_slots);
+
+/* Host-side plan compiler (all pointers HOST memory).  Pass 1 sizes the arrays; pass 2 fills them:
+ * tiles[n_tiles], groups[n_groups], lanes[n_groups][CGB_MEAS_CHUNKS][32], tile_bonds[n_tile_bonds],
+ * col_out[M] (position of every column in the values row; wide columns follow the staged ones, in kind
+ * order) and wide_cols[n_wide] (the columns left to cgb_measure). */
+int cgb_measure_plan_size(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
+                          int64_t n_beads, int32_t max_span, int32_t max_slots, CgbMeasPlanInfo* info);
+int cgb_measure_plan_build(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
+                           int64_t n_beads, int32_t max_span, int32_t max_slots, CgbMeasTile* tiles,
+                           CgbMeasGroup* groups, CgbMeasLane* lanes, int32_t* tile_bonds, int32_t* col_out,
+                           int64_t* wide_cols);
+
+/* Benchmarking knobs of K2, passed per call (NULL or a zero field keeps the default). */
+typedef struct CgbMeasureTuning {
+    int32_t stage_bytes;   /* bytes per pipeline stage                                                    */
+    int32_t n_stages;      /* pipeline depth (2..4)                                                       */
+    int32_t max_run;       /* frames a lane accumulates in float32 before its CTA reduces in float64      */
+    int32_t waves;         /* CTAs per resident slot when the frames provide the parallelism              */
+    int32_t reserved[4];
+} CgbMeasureTuning;
+
+/* K2: one launch for all columns of the plan (device copies of its arrays). */
+int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
+                      const CgbMeasTile* tiles, int64_t n_tiles, const CgbMeasGroup* groups,
+                      const CgbMeasLane* lanes, const int32_t* tile_bonds, int32_t max_span, int32_t max_slots,
+                      int32_t max_edge_chunks, int32_t max_tile_groups, const float* shift, float* values,
+                      int64_t row_stride, double* partials, double* hist, const float* hist_lo,
+                      const float* hist_hi, int32_t n_bins, const CgbMeasureTuning* tuning, void* stream);
+
+/* ---- gather kernels: columns straight from global memory (wide columns, or callers without a plan) ----
+ * col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one
  * kind (a kind with fewer columns is one group) the distinct Bonds are numbered 0, 1, ... in any order and
  * col_slot[c] is the number of column c's Bond; max_slots is the largest count over all groups.  It lets a
- * CTA keep its per-Bond sums and histograms in shared memory sized by the group, not by the system.
- * NULL (or max_slots too large for shared memory) selects global atomics. */
+ * CTA keep its per-Bond sums and histograms in shared memory.  NULL selects global atomics. */
 #define CGB_MEASURE_TILE 224
-/* tile_span: device int32 [T][2] or NULL, T = sum over kinds of ceil(n_kind / CGB_MEASURE_TILE), one row per
- * group in kind order: (first bead, number of beads) of the contiguous bead range that contains every bead
- * of the group's columns; max_span = the largest number of beads.  With tile_span (and col_slot) the staged
- * kernels run: the range is streamed through shared memory with bulk copies and gathered with LDS.  NULL, or
- * a range too large for shared memory, selects the kernels that gather from global memory. */
-
 int cgb_measure(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
                 const int32_t* col_beads, const int32_t* col_bond, const int32_t* col_slot, int32_t max_slots,
-                const int32_t* tile_span, int32_t max_span, int64_t n2, int64_t n3, int64_t n4,
-                int64_t n_bonds, const float* shift, float* values, double* partials,
-                unsigned long long* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
+                int64_t n2, int64_t n3, int64_t n4, const float* shift, float* values, int64_t row_stride,
+                double* partials, double* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
                 void* stream);
 
-/* Benchmarking knobs of the staged K2 kernels: bytes per pipeline stage (1 KiB .. 48 KiB) and pipeline
- * depth (2 .. 4).  Not needed for correctness. */
-int cgb_measure_set_tuning(int32_t stage_bytes, int32_t n_stages);
+/* shift[b] = value of Bond b's first instance in frame `frame` (bond_beads: device int32 [n_bonds][4], natoms:
+ * device int32 [n_bonds], 0 for a Bond without instances), 0 when it is not finite.  Evaluated with the routines
+ * of the measurement kernels, so samples identical to it give d == 0 exactly. */
+int cgb_measure_shift(const float* cg_xyz, const float* box_vec, int ortho, int64_t frame, int64_t n_frames,
+                      int64_t n_beads, const int32_t* bond_beads, const int32_t* natoms, int64_t n_bonds,
+                      float* shift, void* stream);
 
 /* Pass 2 for dihedral columns: partials[b][5] += sum over the bond's values of wrap(v - m_b)^2 with
- * m_b = atan2(partials[b][4], partials[b][3]) (util.py:40-53).  Call after partials[.][3..4] are final
- * (i.e. after the cross-GPU reduction).  values: device pointer to the first of n_cols columns of a
- * [F][row_stride] matrix (the dihedral plane: values + F*(n2+n3), row_stride = n4); col_bond: the Bond of
- * each of those columns (col_bond + n2 + n3). */
-int cgb_circular_pass2(const float* values, int64_t n_frames, int64_t row_stride,
-                       const int32_t* col_bond, int64_t n_cols, double* partials, void* stream);
+ * m_b = atan2(partials[b][4], partials[b][3]) (util.py:40-53), for the Bonds with flags[b * flag_stride] != 0
+ * (all Bonds when flags == NULL).  Call after partials[.][3..4] are final (i.e. after the cross-GPU
+ * reduction).  values: device pointer to the first of n_cols columns of a [F][row_stride] matrix; col_bond:
+ * the Bond of each of those columns. */
+int cgb_circular_pass2(const float* values, int64_t n_frames, int64_t row_stride, const int32_t* col_bond,
+                       int64_t n_cols, double* partials, const double* flags, int64_t flag_stride, void* stream);
 
 /* Statistics of a caller-supplied value array for ONE Bond (Bond.boltzmann_invert on values that were
  * not measured by cgb_measure, bondset.py:72-74): accumulates slots [0..4] and [6] of one partials row.
@@ -192,11 +273,22 @@ int cgb_value_stats(const float* values, int64_t n, int natoms, float shift, dou
 /* ------------------------------------------------------------------------------------------------
  * Stage 3: Boltzmann inversion (one thread per Bond).
  *   natoms[b] in {2,3,4}; form[b] is a CGB_FORM_* id; RT = 8.314 * temperature / 1000.
- *   out: device float64 [n_bonds][4] = { eqm, fconst, mean, variance }
+ *   out: device float64 [n_bonds][CGB_NOUT] = { eqm, fconst, mean, variance, flag }
  *   lengths: arithmetic mean / population variance; angles and dihedrals: circular mean / variance;
  *   dihedral eqm = ((mean) mod 2pi) - pi (bondset.py:81-84); variance == 0 -> fconst = +inf
- *   (bondset.py:89-91); a bond with no finite values yields NaN in all four slots.
+ *   (bondset.py:89-91); a bond with no finite values yields NaN in the first four slots.
+ *
+ * Dihedral variance in one pass: with d = wrap(v - shift) and e = wrap(mean - shift),
+ * <wrap(v - mean)^2> = <d^2> - 2 e <d> + e^2 provided no sample lies on the arc between the antipodes of the
+ * shift and of the mean.  The histogram of the Bond (hist / hist_lo / hist_hi / n_bins as in stage 2; it must
+ * hold every finite sample) proves that: the bins that touch the arc, widened by one bin, must be empty.
+ * Otherwise -- or without a histogram, unless e == 0 -- flag = 1 and the caller runs cgb_circular_pass2 (or
+ * measures again with shift = mean) and calls cgb_boltzmann with pass2 != 0.
+ *   pass2 = 0: one-pass variance, flag output as above;
+ *   pass2 = 1: dihedral Bonds whose out[b][4] is non-zero ON ENTRY take partials[b][5] / n (flag becomes 2);
+ *   pass2 = 2: every dihedral Bond takes partials[b][5] / n.
  * ---------------------------------------------------------------------------------------------- */
+#define CGB_NOUT 5
 enum {
     CGB_FORM_HARMONIC = 0,            /* RT / var                       functionalforms.py:101-104 */
     CGB_FORM_COSHARMONIC = 1,         /* RT / (sin^2(mean) * var)       functionalforms.py:117-121 */
@@ -207,7 +299,24 @@ enum {
 };
 
 int cgb_boltzmann(const double* partials, const float* shift, const int32_t* natoms, const int32_t* form,
-                  double temperature, int64_t n_bonds, double* out, void* stream);
+                  double temperature, int64_t n_bonds, const double* hist, const float* hist_lo,
+                  const float* hist_hi, int32_t n_bins, int pass2, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross-GPU exchange (one process per GPU, frames sharded by rank): the only state that crosses GPUs is the
+ * packed float64 buffer [partials | hist].  These entry points wrap NCCL (libnccl.so.2, resolved at run time
+ * with dlopen so that the library loads without it); the reference has no counterpart (single process).
+ *   cgb_comm_unique_id : rank 0 creates the 128-byte id, the caller distributes it to the other ranks;
+ *   cgb_comm_init      : collective over all ranks, on the current CUDA device;
+ *   cgb_allreduce_partials : ncclAllReduce(sum, float64) in place on `stream`, no host synchronisation;
+ *   cgb_comm_broadcast : ncclBroadcast of raw bytes from `root` (the shift of the statistics).
+ * ---------------------------------------------------------------------------------------------- */
+#define CGB_COMM_ID_BYTES 128
+int cgb_comm_unique_id(uint8_t* id);
+int cgb_comm_init(const uint8_t* id, int32_t rank, int32_t world_size, void** comm);
+int cgb_comm_destroy(void* comm);
+int cgb_allreduce_partials(void* comm, double* packed, int64_t count, void* stream);
+int cgb_comm_broadcast(void* comm, void* buffer, int64_t n_bytes, int32_t root, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Trajectory ingest: GROMACS .xtc (the caller of the hot path, reference pycgtool/frame.py:41-63, where the

@@ -11,7 +11,13 @@ _CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIBRARY_PATH = _CSRC / "libpycgtool_b200.so"
 
 NPART = 8  # CGB_NPART
+NOUT = 5  # CGB_NOUT
 MEASURE_TILE = 224  # CGB_MEASURE_TILE
+MEAS_WARPS = 7  # CGB_MEAS_WARPS
+MEAS_CHUNKS = 4  # CGB_MEAS_CHUNKS
+MEAS_EDGE_CHUNKS = 2  # CGB_MEAS_EDGE_CHUNKS
+COMM_ID_BYTES = 128  # CGB_COMM_ID_BYTES
+ABI_VERSION = 2  # CGB_ABI_VERSION
 
 FORM_IDS = {
     "Harmonic": 0,
@@ -24,6 +30,51 @@ FORM_STATS_ONLY = 5
 
 
 XTC_FRAME_BYTES = 48  # sizeof(CgbXtcFrame)
+
+
+class MeasPlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_tiles", ctypes.c_int64),
+        ("n_groups", ctypes.c_int64),
+        ("n_tile_bonds", ctypes.c_int64),
+        ("n_wide", ctypes.c_int64),
+        ("n_staged", ctypes.c_int64),
+        ("max_span", ctypes.c_int32),
+        ("max_slots", ctypes.c_int32),
+        ("max_edge_chunks", ctypes.c_int32),
+        ("max_tile_groups", ctypes.c_int32),
+    ]
+
+
+class MapTuning(ctypes.Structure):
+    """``CgbMapTuning``: per-call benchmarking knobs of K1 (zero keeps the default)."""
+    _fields_ = [
+        ("stage_bytes", ctypes.c_int32),
+        ("n_stages", ctypes.c_int32),
+        ("frames_per_cta", ctypes.c_int32),
+        ("consumer_threads", ctypes.c_int32),
+        ("frame_group", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 3),
+    ]
+
+
+class MeasureTuning(ctypes.Structure):
+    """``CgbMeasureTuning``: per-call benchmarking knobs of K2 (zero keeps the default)."""
+    _fields_ = [
+        ("stage_bytes", ctypes.c_int32),
+        ("n_stages", ctypes.c_int32),
+        ("max_run", ctypes.c_int32),
+        ("waves", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+#: numpy dtypes of the plan structs of include/pycgtool_b200.h (CgbMeasTile, CgbMeasGroup, CgbMeasLane)
+MEAS_TILE_DTYPE = [("bead0", "<i4"), ("span", "<i4"), ("group0", "<i4"), ("ngroups", "<i4"),
+                   ("slot0", "<i4"), ("nslots", "<i4"), ("reserved", "<i4", (2,))]
+MEAS_GROUP_DTYPE = [("kind", "u1", (4,)), ("nlanes", "u1", (4,)), ("nemit", "u1", (4,)),
+                    ("vcol0", "<i4", (4,)), ("reserved", "<i4")]
+MEAS_LANE_DTYPE = [("ref", "<u4"), ("slot", "<i4")]
 
 
 class MapTile(ctypes.Structure):
@@ -53,14 +104,23 @@ SIGNATURES = {
     "cgb_map_tiles_window": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "cgb_copy_window_h2d": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
-    "cgb_map_set_tuning": (_int, [_i32, _i32, _i32]),
-    "cgb_map_set_shape": (_int, [_i32, _i32]),
-    "cgb_measure_set_tuning": (_int, [_i32, _i32]),
-    "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64,
-                           _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "cgb_map_tiles_ex": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "cgb_measure_plan_limits": (_int, [_i32, _int, _vp, _vp]),
+    "cgb_measure_plan_size": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cgb_measure_fused": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i64, _i64,
+                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "cgb_measure_shift": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "cgb_circular_pass2": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp]),
     "cgb_value_stats": (_int, [_vp, _i64, _int, ctypes.c_float, _vp, _vp]),
-    "cgb_boltzmann": (_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _i64, _vp, _vp]),
+    "cgb_boltzmann": (_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _i64, _vp, _vp, _vp, _i32, _int, _vp, _vp]),
+    "cgb_comm_unique_id": (_int, [_vp]),
+    "cgb_comm_init": (_int, [_vp, _i32, _i32, _vp]),
+    "cgb_comm_destroy": (_int, [_vp]),
+    "cgb_allreduce_partials": (_int, [_vp, _vp, _i64, _vp]),
+    "cgb_comm_broadcast": (_int, [_vp, _vp, _i64, _i32, _vp]),
     "cgb_xtc_scan": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cgb_xtc_workspace_bytes": (_i64, [_i64, _i64]),
     "cgb_xtc_decode": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),
@@ -85,7 +145,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.cgb_abi_version() != 1:
+    if lib.cgb_abi_version() != ABI_VERSION:
         raise RuntimeError("libpycgtool_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -96,6 +156,11 @@ def check(code, what="libpycgtool_b200 call"):
     if code != 0:
         text = load().cgb_strerror(code).decode()
         raise RuntimeError(f"{what} failed with code {code}: {text}")
+
+
+def tuning_ptr(tuning):
+    """``ctypes`` pointer of a tuning struct, or None (built-in defaults)."""
+    return None if tuning is None else ctypes.cast(ctypes.pointer(tuning), ctypes.c_void_p)
 
 
 def ptr(array):

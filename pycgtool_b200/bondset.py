@@ -66,9 +66,9 @@ class Bond:
         """Equilibrium value and force constant from the measured values (``bondset.py:62-91``)."""
         if self._source is not None:
             state, bond_id = self._source
-            if state.n_values(bond_id) == 0:
+            state.invert(temp)      # collective when frames are sharded: every rank enters before any early exit
+            if state.n_values_global(bond_id) == 0:
                 raise ValueError("No bonds were measured between beads {0}".format(self.atoms))
-            state.invert(temp)
             state.assign(self, bond_id, temp)
             return
         if len(self.values) == 0:
@@ -126,19 +126,19 @@ def _stats_of_values(values, natoms):
     if natoms == 4:
         zero = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.check(lib.cgb_circular_pass2(device.dptr(vals), len(values), 1, device.dptr(zero), 1,
-                                          device.dptr(row), stream), "cgb_circular_pass2")
-    out = torch.empty(4, dtype=torch.float64, device=dev)
+                                          device.dptr(row), None, 0, stream), "cgb_circular_pass2")
+    out = torch.empty(_lib.NOUT, dtype=torch.float64, device=dev)
     nat = torch.tensor([natoms], dtype=torch.int32, device=dev)
     form = torch.tensor([_lib.FORM_STATS_ONLY], dtype=torch.int32, device=dev)
     sh = torch.tensor([shift], dtype=torch.float32, device=dev)
     _lib.check(lib.cgb_boltzmann(device.dptr(row), device.dptr(sh), device.dptr(nat), device.dptr(form),
-                                 310.0, 1, device.dptr(out), stream), "cgb_boltzmann")
+                                 310.0, 1, None, None, None, 0, 2, device.dptr(out), stream), "cgb_boltzmann")
     res = out.cpu().numpy()
     return float(res[2]), float(res[3])
 
 
 class MeasurePlan:
-    """Integer column table for one (bond set, topology) pair."""
+    """Integer tables for one (bond set, topology) pair: the columns and the fused kernel's plan."""
 
     def __init__(self):
         self.n_beads = 0
@@ -146,47 +146,91 @@ class MeasurePlan:
         self.counts = (0, 0, 0)       # columns per kind (lengths, angles, dihedrals)
         self.col_beads = None         # int32 (M, 4)
         self.col_bond = None          # int32 (M,)
-        self.col_slot = None          # int32 (M,) compact Bond number inside each tile of _lib.MEASURE_TILE columns of a kind
-        self.max_slots = 0
-        self.tile_span = None         # int32 (T, 2): (first bead, beads) of the range each tile gathers from
-        self.max_span = 0
-        self.bond_cols = []           # per bond: int64 column ids in instance order
+        self.bond_cols = []           # per bond: int64 positions in the values row, in instance order
+        self.bond_columns = []        # per bond: int64 column numbers (rows of col_beads), in instance order
         self.bond_indices = []        # per bond: int32 (n_inst, natoms) -- what mdtraj would receive
         self.natoms = None            # int32 (n_bonds,)
+        self.bond_first = None        # int32 (n_bonds, 4): beads of each bond's first instance
+        self.natoms_measured = None   # int32 (n_bonds,): natoms, 0 for a bond without instances
+        # fused kernel (cgb_measure_fused): structured arrays mirroring include/pycgtool_b200.h
+        self.tiles = self.groups = self.lanes = self.tile_bonds = None
+        self.n_staged = 0             # columns [0, n_staged) of the values row come from the fused kernel
+        self.max_span = self.max_slots = self.max_edge_chunks = self.max_tile_groups = 0
+        self.col_out = None           # int32 (M,): position of every column in the values row
+        # gather kernels (cgb_measure): columns whose beads are too far apart for a tile, in kind order
+        self.wide_counts = (0, 0, 0)
+        self.wide_beads = self.wide_bond = self.wide_slot = None
+        self.wide_max_slots = 0
         self._dev = {}
+
+    @property
+    def n_cols(self):
+        return int(sum(self.counts))
 
 
 class _MeasureState:
-    """Device buffers of one ``BondSet.apply`` call."""
+    """Device buffers of one ``BondSet.apply`` call.
 
-    def __init__(self, bondset, plan, n_frames, values, partials, hist, shift, hist_lo, hist_hi, dev):
+    ``packed`` is ONE float64 buffer ``[partials (n_bonds, 8) | hist (n_bonds, nbins)]``: the only state
+    that crosses GPUs, summed with a single all-reduce.
+    """
+
+    def __init__(self, bondset, plan, n_frames, values, packed, nbins, shift, hist_lo, hist_hi, dev, source):
         self.bondset, self.plan, self.n_frames = bondset, plan, n_frames
-        self.values, self.partials, self.hist, self.shift = values, partials, hist, shift
+        self.values, self.packed, self.shift = values, packed, shift
+        npart = plan.n_bonds * _lib.NPART
+        self.partials = packed[:npart].view(plan.n_bonds, _lib.NPART)
+        self.hist = packed[npart:].view(plan.n_bonds, nbins) if nbins else None
         self.hist_lo, self.hist_hi = hist_lo, hist_hi
         self.dev = dev
+        self.source = source        # (xyz, box, ortho) on the device: lets `.values` be measured on demand
         self.reduced = False
         self.result = None
         self.result_temp = None
         self.hist_host = None
+        self.counts_host = None     # (n_bonds,) number of values over all ranks (finite or not)
 
     def n_values(self, bond_id):
         return self.n_frames * len(self.plan.bond_cols[bond_id])
+
+    def n_values_global(self, bond_id):
+        """Values of the bond over all ranks (known after ``invert``)."""
+        if self.counts_host is None:
+            return self.n_values(bond_id)
+        return int(self.counts_host[bond_id])
 
     def fetch_values(self, bond_id):
         import torch
         cols = self.plan.bond_cols[bond_id]
         if len(cols) == 0 or self.n_frames == 0:
             return np.zeros(0, dtype=np.float32)
-        # values are stored as one (F, n_kind) plane per kind (see include/pycgtool_b200.h)
-        n2, n3, n4 = self.plan.counts
-        kind = int(self.plan.natoms[bond_id])
-        col0, n_k = {2: (0, n2), 3: (n2, n3), 4: (n2 + n3, n4)}[kind]
-        plane = self.values[self.n_frames * col0:self.n_frames * (col0 + n_k)].view(self.n_frames, n_k)
-        idx = torch.from_numpy(cols - col0).to(self.dev)
-        return plane.index_select(1, idx).reshape(-1).cpu().numpy()
+        if self.values is None:
+            # statistics-only pass: measure the values now (into scratch accumulators)
+            self.values = torch.empty((self.n_frames, self.plan.n_cols), dtype=torch.float32, device=self.dev)
+            scratch = torch.zeros_like(self.packed)
+            self.bondset._launch_measure(self.plan, self.source, self.n_frames, self.shift, self.values, scratch,
+                                         0, None, None)
+        idx = torch.from_numpy(cols).to(self.dev)
+        return self.values.index_select(1, idx).reshape(-1).cpu().numpy()
+
+    def _boltzmann(self, temp, pass2, out):
+        lib = _lib.load()
+        plan = self.plan
+        d = BondSet._device_plan(plan, self.dev)
+        nbins = 0 if self.hist is None else int(self.hist.shape[1])
+        _lib.check(lib.cgb_boltzmann(device.dptr(self.partials), device.dptr(self.shift), device.dptr(d["natoms"]),
+                                     device.dptr(d["forms"]), float(temp), plan.n_bonds, device.dptr(self.hist),
+                                     device.dptr(self.hist_lo), device.dptr(self.hist_hi), nbins, pass2,
+                                     device.dptr(out), device.stream_handle()), "cgb_boltzmann")
 
     def invert(self, temp):
-        """Cross-GPU reduction, dihedral pass 2 and the epilogue kernel (idempotent per ``temp``)."""
+        """Cross-GPU reduction and the epilogue kernel (idempotent per ``temp``).
+
+        Common case: one all-reduce of the packed buffer, one epilogue launch, one device-to-host copy.  Only
+        when a dihedral Bond has samples next to the antipode of its mean (its one-pass circular variance is
+        then flagged inexact) does a second pass run: over the stored values, or -- statistics-only -- a second
+        measurement about the now known mean.
+        """
         import torch
         if self.result is not None and self.result_temp == temp:
             return
@@ -194,39 +238,58 @@ class _MeasureState:
         plan = self.plan
         stream = device.stream_handle()
         d = BondSet._device_plan(plan, self.dev)
-        n2, n3, n4 = plan.counts
         if not self.reduced:
-            # frames are sharded across GPUs: sum the per-bond moments (and histograms) once
-            dist.allreduce_sum(self.partials)
-            if self.hist is not None:
-                dist.allreduce_sum(self.hist)
-            if n4:
-                # dihedrals: the circular mean is final now, so finish <wrap(v - mean)^2> (util.py:49-53)
-                plane4 = self.values[self.n_frames * (n2 + n3):]
-                _lib.check(lib.cgb_circular_pass2(device.dptr(plane4), self.n_frames, n4,
-                                                  device.dptr(d["col_bond"][n2 + n3:]), n4,
-                                                  device.dptr(self.partials), stream), "cgb_circular_pass2")
+            dist.allreduce_packed(self.packed)      # frames are sharded across GPUs: one sum of [moments | hist]
+            self.reduced = True
+        out = torch.empty((plan.n_bonds, _lib.NOUT), dtype=torch.float64, device=self.dev)
+        self._boltzmann(temp, 0, out)
+        host = torch.cat([out.reshape(-1), self.partials[:, 6]]).cpu().numpy()
+        result = host[:plan.n_bonds * _lib.NOUT].reshape(plan.n_bonds, _lib.NOUT)
+        self.counts_host = host[plan.n_bonds * _lib.NOUT:].astype(np.int64)
+        flagged = np.nonzero(result[:, 4] == 1.0)[0]
+        if len(flagged):
+            n_cols = plan.n_cols
+            if self.values is not None:
+                # exact <wrap(v - mean)^2> of the flagged Bonds over the stored values (util.py:49-53)
+                self.partials[:, 5].zero_()
+                if n_cols and self.n_frames:
+                    _lib.check(lib.cgb_circular_pass2(device.dptr(self.values), self.n_frames, n_cols,
+                                                      device.dptr(d["col_bond_by_pos"]), n_cols,
+                                                      device.dptr(self.partials), device.dptr(out[:, 4:]),
+                                                      _lib.NOUT, stream), "cgb_circular_pass2")
                 if dist.is_distributed():
                     wrapped = self.partials[:, 5].contiguous()
-                    dist.allreduce_sum(wrapped)
+                    dist.allreduce_packed(wrapped)
                     self.partials[:, 5] = wrapped
-            self.reduced = True
-        out = torch.empty((plan.n_bonds, 4), dtype=torch.float64, device=self.dev)
-        _lib.check(lib.cgb_boltzmann(device.dptr(self.partials), device.dptr(self.shift), device.dptr(d["natoms"]),
-                                     device.dptr(d["forms"]), float(temp), plan.n_bonds, device.dptr(out), stream),
-                   "cgb_boltzmann")
-        self.result = out.cpu().numpy()
+                self._boltzmann(temp, 1, out)
+            else:
+                # statistics only: measure again about the mean (then e == 0 and the one-pass sum is exact)
+                mean32 = out[:, 2].to(torch.float32)
+                pick = torch.zeros(plan.n_bonds, dtype=torch.bool, device=self.dev)
+                pick[torch.from_numpy(flagged).to(self.dev)] = True
+                self.shift = torch.where(pick, mean32, self.shift).contiguous()
+                again = torch.zeros_like(self.packed)
+                nbins = 0 if self.hist is None else int(self.hist.shape[1])
+                self.bondset._launch_measure(plan, self.source, self.n_frames, self.shift, None, again, nbins,
+                                             self.hist_lo, self.hist_hi)
+                dist.allreduce_packed(again)
+                npart = plan.n_bonds * _lib.NPART
+                fresh = again[:npart].view(plan.n_bonds, _lib.NPART)
+                self.partials[pick] = fresh[pick]
+                self._boltzmann(temp, 0, out)
+            result = out.cpu().numpy()
+        self.result = result
         self.result_temp = temp
         if self.hist is not None and self.hist_host is None:
-            self.hist_host = self.hist.cpu().numpy().view(np.uint64)
+            self.hist_host = np.rint(self.hist.cpu().numpy()).astype(np.uint64)
 
     def assign(self, bond, bond_id, temp):
-        eqm, fconst, mean, var = (float(x) for x in self.result[bond_id])
+        eqm, fconst, mean, var = (float(x) for x in self.result[bond_id][:4])
         if math.isnan(mean):
             return          # nothing finite was measured: leave eqm / fconst as None
         _finish_bond(bond, mean, var, temp, device_result=(eqm, fconst))
         if self.hist_host is not None:
-            edges = np.linspace(float(self.hist_lo[bond_id]), float(self.hist_hi[bond_id]),
+            edges = np.linspace(float(self.hist_lo_host[bond_id]), float(self.hist_hi_host[bond_id]),
                                 self.hist_host.shape[1] + 1)
             bond.histogram = (self.hist_host[bond_id].copy(), edges)
 
@@ -254,7 +317,8 @@ class BondSet:
         self._functional_forms = self._get_default_func_forms(options)
         self.histogram_bins = getattr(options, "histogram_bins", HIST_BINS)
         self.histogram_ranges = dict(HIST_RANGES)
-        self.staged = True            # stream bead tiles through shared memory (False: gather from global)
+        self.staged = True            # fused kernel over shared-memory tiles (False: gather from global)
+        self.tuning = None            # optional _lib.MeasureTuning, passed to every cgb_measure_fused call
         self._plans = {}
         self._state = None
 
@@ -464,35 +528,69 @@ class BondSet:
                 start += len(t)
             offset += n_k
         plan.counts = tuple(counts)
-        plan.col_beads = (np.concatenate(col_beads, axis=0) if col_beads else np.zeros((0, 4))).astype(np.int32)
-        plan.col_bond = (np.concatenate(col_bond) if col_bond else np.zeros(0)).astype(np.int32)
-        plan.col_slot, plan.max_slots = self._tile_slots(plan.col_bond, plan.counts)
-        plan.tile_span, plan.max_span = self._tile_spans(plan.col_beads, plan.counts)
+        plan.col_beads = np.ascontiguousarray(
+            np.concatenate(col_beads, axis=0) if col_beads else np.zeros((0, 4)), dtype=np.int32)
+        plan.col_bond = np.ascontiguousarray(np.concatenate(col_bond) if col_bond else np.zeros(0), dtype=np.int32)
+        plan.bond_first = np.zeros((plan.n_bonds, 4), dtype=np.int32)
+        plan.natoms_measured = np.zeros(plan.n_bonds, dtype=np.int32)
+        for b, cols in enumerate(plan.bond_cols):
+            if len(cols):
+                plan.bond_first[b] = plan.col_beads[cols[0]]
+                plan.natoms_measured[b] = plan.natoms[b]
+        self._compile_kernel_plan(plan)
+        # from column numbers to positions in the values row
+        plan.bond_columns = plan.bond_cols
+        plan.bond_cols = [plan.col_out[cols].astype(np.int64) for cols in plan.bond_columns]
         return plan
 
-    @staticmethod
-    def _tile_spans(col_beads, counts):
-        """Contiguous bead range covering each tile of ``CGB_MEASURE_TILE`` columns (staged kernels)."""
-        tile = _lib.MEASURE_TILE
-        rows, start = [], 0
-        for n_k in counts:
-            if n_k:
-                block = col_beads[start:start + n_k]
-                lo, hi = block.min(axis=1), block.max(axis=1)
-                cuts = np.arange(0, n_k, tile)
-                first = np.minimum.reduceat(lo, cuts)
-                last = np.maximum.reduceat(hi, cuts)
-                rows.append(np.stack([first, last - first + 1], axis=1))
-            start += n_k
-        if not rows:
-            return np.zeros((0, 2), dtype=np.int32), 0
-        spans = np.concatenate(rows, axis=0).astype(np.int32)
-        return spans, int(spans[:, 1].max())
+    def _compile_kernel_plan(self, plan):
+        """Tiles / groups / lanes of the fused kernel (``cgb_measure_plan_*``, host code in the library) and the
+        sub-table of the columns left to the gather kernels."""
+        import ctypes
+        lib = _lib.load()
+        n2, n3, n4 = plan.counts
+        n_cols = n2 + n3 + n4
+        nbins = int(self.histogram_bins)
+        max_span, max_slots = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(lib.cgb_measure_plan_limits(nbins, 1, ctypes.byref(max_span), ctypes.byref(max_slots)),
+                   "cgb_measure_plan_limits")
+        plan.col_out = np.arange(n_cols, dtype=np.int32)
+        wide = np.arange(n_cols, dtype=np.int64)
+        plan.tiles = np.zeros(0, dtype=_lib.MEAS_TILE_DTYPE)
+        plan.groups = np.zeros(0, dtype=_lib.MEAS_GROUP_DTYPE)
+        plan.lanes = np.zeros(0, dtype=_lib.MEAS_LANE_DTYPE)
+        plan.tile_bonds = np.zeros(0, dtype=np.int32)
+        if self.staged and n_cols:
+            info = _lib.MeasPlanInfo()
+            # Bonds per tile: what the largest molecule needs (a tile then never mixes molecule types, which keeps
+            # its shared-memory histograms small), within what fits
+            per_molecule = max([len(bonds) for bonds in self._molecules.values()] + [1])
+            slots = min(max_slots.value, max(per_molecule, 8))
+            args = (_lib.ptr(plan.col_beads), _lib.ptr(plan.col_bond), n2, n3, n4, plan.n_beads,
+                    max_span.value, slots)
+            _lib.check(lib.cgb_measure_plan_size(*args, ctypes.byref(info)), "cgb_measure_plan_size")
+            plan.tiles = np.zeros(info.n_tiles, dtype=_lib.MEAS_TILE_DTYPE)
+            plan.groups = np.zeros(info.n_groups, dtype=_lib.MEAS_GROUP_DTYPE)
+            plan.lanes = np.zeros(info.n_groups * _lib.MEAS_CHUNKS * 32, dtype=_lib.MEAS_LANE_DTYPE)
+            plan.tile_bonds = np.zeros(info.n_tile_bonds, dtype=np.int32)
+            wide = np.zeros(info.n_wide, dtype=np.int64)
+            _lib.check(lib.cgb_measure_plan_build(*args, _lib.ptr(plan.tiles), _lib.ptr(plan.groups),
+                                                  _lib.ptr(plan.lanes), _lib.ptr(plan.tile_bonds),
+                                                  _lib.ptr(plan.col_out), _lib.ptr(wide)), "cgb_measure_plan_build")
+            plan.n_staged = int(info.n_staged)
+            plan.max_span, plan.max_slots = int(info.max_span), int(info.max_slots)
+            plan.max_edge_chunks, plan.max_tile_groups = int(info.max_edge_chunks), int(info.max_tile_groups)
+        # wide columns keep their kind order; they follow the staged columns in the values row
+        w_counts = (int((wide < n2).sum()), int(((wide >= n2) & (wide < n2 + n3)).sum()), int((wide >= n2 + n3).sum()))
+        plan.wide_counts = w_counts
+        plan.wide_beads = np.ascontiguousarray(plan.col_beads[wide])
+        plan.wide_bond = np.ascontiguousarray(plan.col_bond[wide])
+        plan.wide_slot, plan.wide_max_slots = self._tile_slots(plan.wide_bond, w_counts)
 
     @staticmethod
     def _tile_slots(col_bond, counts):
         """Number the distinct Bonds inside every tile of ``CGB_MEASURE_TILE`` consecutive columns of a
-        kind (see ``include/pycgtool_b200.h``): the measurement CTAs keep per-Bond sums and histograms
+        kind (see ``include/pycgtool_b200.h``): the gather CTAs keep per-Bond sums and histograms
         in shared memory indexed by this compact slot."""
         tile = _lib.MEASURE_TILE
         slots = np.zeros(len(col_bond), dtype=np.int32)
@@ -513,7 +611,7 @@ class BondSet:
         return slots, max_slots
 
     def _plan_for(self, topology):
-        key = id(topology)
+        key = (id(topology), bool(self.staged), int(self.histogram_bins))
         cached = self._plans.get(key)
         if cached is None or cached[0] is not topology or cached[1].n_beads != topology.n_atoms:
             cached = (topology, self.compile_plan(topology))
@@ -531,59 +629,89 @@ class BondSet:
     def _device_plan(plan, dev):
         key = str(dev)
         if key not in plan._dev:
+            by_pos = np.zeros(plan.n_cols, dtype=np.int32)
+            by_pos[plan.col_out] = plan.col_bond
             plan._dev[key] = {
-                "col_beads": device.to_device(plan.col_beads, dev),
-                "col_bond": device.to_device(plan.col_bond, dev),
-                "col_slot": device.to_device(plan.col_slot, dev),
-                "tile_span": device.to_device(plan.tile_span, dev),
+                "tiles": device.to_device(plan.tiles.view(np.int32), dev),
+                "groups": device.to_device(plan.groups.view(np.int32), dev),
+                "lanes": device.to_device(plan.lanes.view(np.int32), dev),
+                "tile_bonds": device.to_device(plan.tile_bonds, dev),
+                "wide_beads": device.to_device(plan.wide_beads, dev),
+                "wide_bond": device.to_device(plan.wide_bond, dev),
+                "wide_slot": device.to_device(plan.wide_slot, dev),
+                "col_bond_by_pos": device.to_device(by_pos, dev),
+                "bond_first": device.to_device(plan.bond_first, dev),
+                "natoms_measured": device.to_device(plan.natoms_measured, dev),
                 "natoms": device.to_device(plan.natoms, dev),
             }
         return plan._dev[key]
 
+    def _launch_measure(self, plan, source, n_frames, shift, values, packed, nbins, hist_lo, hist_hi):
+        """Enqueue the measurement of all columns: the fused kernel, then the gather kernels for wide columns.
+        ``values`` None = statistics only; ``nbins`` 0 = no histogram."""
+        lib = _lib.load()
+        xyz, box_dev, ortho = source
+        dev = xyz.device
+        d = self._device_plan(plan, dev)
+        stream = device.stream_handle()
+        npart = plan.n_bonds * _lib.NPART
+        partials = packed[:npart]
+        hist = packed[npart:] if nbins else None
+        n_cols = plan.n_cols
+        if len(plan.tiles):
+            _lib.check(lib.cgb_measure_fused(
+                device.dptr(xyz), device.dptr(box_dev), ortho, n_frames, plan.n_beads, device.dptr(d["tiles"]),
+                len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]), device.dptr(d["tile_bonds"]),
+                plan.max_span, plan.max_slots, plan.max_edge_chunks, plan.max_tile_groups, device.dptr(shift),
+                device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist), device.dptr(hist_lo),
+                device.dptr(hist_hi), int(nbins), _lib.tuning_ptr(self.tuning), stream), "cgb_measure_fused")
+        w2, w3, w4 = plan.wide_counts
+        if w2 + w3 + w4:
+            wide_values = None if values is None else values.view(-1)[plan.n_staged:]
+            _lib.check(lib.cgb_measure(
+                device.dptr(xyz), device.dptr(box_dev), ortho, n_frames, plan.n_beads, device.dptr(d["wide_beads"]),
+                device.dptr(d["wide_bond"]), device.dptr(d["wide_slot"]), plan.wide_max_slots, w2, w3, w4,
+                device.dptr(shift), device.dptr(wide_values), n_cols, device.dptr(partials), device.dptr(hist),
+                device.dptr(hist_lo), device.dptr(hist_hi), int(nbins), stream), "cgb_measure")
+
     # ------------------------------------------------------------------ apply (bondset.py:496-531)
-    def apply(self, frame, histogram=True):
+    def apply(self, frame, histogram=True, store_values=True):
         """Measure every bonded term in every frame of ``frame`` on the GPU.
 
-        Afterwards each ``bond.values`` is the frame-major float32 array the
-        reference stores (fetched lazily), and the statistics accumulators needed by
-        ``boltzmann_invert`` are already on the device.
+        Afterwards each ``bond.values`` is the frame-major float32 array the reference stores (fetched
+        lazily), and the statistics accumulators needed by ``boltzmann_invert`` are already on the device.
+        ``store_values=False`` is the statistics-only mode: no value is written per measure (the reference
+        only needs them for ``dump_values``, ``bondset.py:562-599``); ``bond.values`` then triggers a
+        measurement of its own on first use.
         """
-        import os
-        import time
         import torch
         device.require_cuda()
         lib = _lib.load()
-        trace = os.environ.get("CGB_TRACE")
-        marks = [("start", time.perf_counter())]
-
-        def mark(label):
-            if trace:
-                torch.cuda.synchronize()
-                marks.append((label, time.perf_counter()))
-
         self._state = None          # release the previous call's buffers before allocating new ones
         plan = self._plan_for(frame._topology)
-        mark("plan")
         traj = frame._trajectory
         xyz = traj.device_xyz()
         dev = xyz.device
         n_frames = int(xyz.shape[0])
-        n2, n3, n4 = plan.counts
-        n_cols = n2 + n3 + n4
+        n_cols = plan.n_cols
         d = self._device_plan(plan, dev)
         if "forms" not in d:
             d["forms"] = device.to_device(self._form_ids(), dev)
 
-        # mdtraj: orthorhombic fast path only if every angle of every frame is ~90 degrees
-        box_dev, ortho = traj.device_box_vectors(dev), int(traj.orthorhombic)
-        mark("box")
+        # mdtraj: orthorhombic fast path only if every angle of every frame is ~90 degrees; with the frames
+        # sharded across GPUs both decisions are taken over the whole trajectory, like the reference's
+        box_dev = traj.device_box_vectors(dev)
+        has_box = dist.all_true(box_dev is not None, device=dev)
+        ortho = int(dist.all_true(bool(traj.orthorhombic), device=dev))
+        if not has_box:
+            box_dev = None
+        source = (xyz, box_dev, ortho)
 
-        values = torch.empty(n_frames * n_cols, dtype=torch.float32, device=dev)   # one plane per kind
-        partials = torch.zeros((plan.n_bonds, _lib.NPART), dtype=torch.float64, device=dev)
-        hist = hist_lo = hist_hi = lo = hi = None
-        if histogram and plan.n_bonds:
-            nbins = int(self.histogram_bins)
-            hist = torch.zeros((plan.n_bonds, nbins), dtype=torch.int64, device=dev)
+        nbins = int(self.histogram_bins) if (histogram and plan.n_bonds) else 0
+        values = torch.empty((n_frames, n_cols), dtype=torch.float32, device=dev) if store_values else None
+        packed = torch.zeros(plan.n_bonds * (_lib.NPART + nbins), dtype=torch.float64, device=dev)
+        hist_lo = hist_hi = lo = hi = None
+        if nbins:
             key = ("hist", tuple(sorted(self.histogram_ranges.items())))
             if key not in d:
                 lo = np.array([self.histogram_ranges[int(k)][0] for k in plan.natoms], dtype=np.float32)
@@ -591,47 +719,24 @@ class BondSet:
                 d[key] = (lo, hi, device.to_device(lo, dev), device.to_device(hi, dev))
             lo, hi, hist_lo, hist_hi = d[key]
         stream = device.stream_handle()
-        mark("alloc")
-
-        def measure(nf, vals, parts, shift, hst):
-            _lib.check(lib.cgb_measure(device.dptr(xyz), device.dptr(box_dev), ortho, nf, plan.n_beads,
-                                       device.dptr(d["col_beads"]), device.dptr(d["col_bond"]),
-                                       device.dptr(d["col_slot"]), plan.max_slots,
-                                       device.dptr(d["tile_span"]) if self.staged else None, plan.max_span,
-                                       n2, n3, n4,
-                                       plan.n_bonds, device.dptr(shift), device.dptr(vals), device.dptr(parts),
-                                       device.dptr(hst), device.dptr(hist_lo), device.dptr(hist_hi),
-                                       int(self.histogram_bins), stream), "cgb_measure")
 
         # Shift for the one-pass variance: each bond's first value in the first frame of rank 0, so
         # that identical samples give exactly zero variance and all shards share the same shift.
-        shift = torch.zeros(plan.n_bonds, dtype=torch.float32, device=dev)
+        shift = torch.empty(plan.n_bonds, dtype=torch.float32, device=dev)
+        _lib.check(lib.cgb_measure_shift(device.dptr(xyz), device.dptr(box_dev), ortho, 0, n_frames, plan.n_beads,
+                                         device.dptr(d["bond_first"]), device.dptr(d["natoms_measured"]),
+                                         plan.n_bonds, device.dptr(shift), stream), "cgb_measure_shift")
+        dist.broadcast_device(shift, src=0)
         if n_cols and n_frames:
-            scratch = torch.zeros_like(partials)
-            measure(1, values, scratch, None, None)
-            if "first_col" not in d:
-                first_col = np.array([cols[0] if len(cols) else 0 for cols in plan.bond_cols], dtype=np.int64)
-                d["first_col"] = device.to_device(first_col, dev)
-                d["has_col"] = device.to_device(np.array([len(cols) > 0 for cols in plan.bond_cols]), dev)
-            has = d["has_col"]
-            # the one-frame pre-pass wrote planes of a 1-frame trajectory: plane offset 1*c0 == column index
-            picked = values[:n_cols].index_select(0, d["first_col"])
-            shift = torch.where(has & torch.isfinite(picked), picked, torch.zeros_like(picked)).contiguous()
-        dist.broadcast(shift, src=0)
-        mark("shift")
-        if n_cols and n_frames:
-            measure(n_frames, values, partials, shift, hist)
-        mark("measure")
+            self._launch_measure(plan, source, n_frames, shift, values, packed, nbins, hist_lo, hist_hi)
 
-        self._state = _MeasureState(self, plan, n_frames, values, partials, hist, shift,
-                                    None if hist is None else lo, None if hist is None else hi, dev)
+        state = _MeasureState(self, plan, n_frames, values, packed, nbins, shift, hist_lo, hist_hi, dev, source)
+        state.hist_lo_host, state.hist_hi_host = lo, hi
+        self._state = state
         for bond_id, bond in enumerate(itertools.chain(*self._molecules.values())):
             bond._values = None
-            bond._source = (self._state, bond_id)
+            bond._source = (state, bond_id)
             bond.eqm = bond.fconst = None
-        if trace:
-            print("BondSet.apply trace:", ", ".join(
-                f"{label} {1e3 * (t - marks[i][1]):.2f} ms" for i, (label, t) in enumerate(marks[1:])))
 
     def boltzmann_invert(self):
         """Equilibrium values and force constants of all bonds (``bondset.py:533-539``)."""
@@ -640,7 +745,7 @@ class BondSet:
         if state is not None and all(b._source is not None and b._source[0] is state for b in bonds):
             state.invert(self._temperature)
             for bond_id, bond in enumerate(bonds):
-                if state.n_values(bond_id):
+                if state.n_values_global(bond_id):
                     state.assign(bond, bond_id, self._temperature)
             return
         for bond in bonds:

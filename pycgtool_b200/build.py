@@ -13,15 +13,16 @@ import shutil
 import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
-SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_boltzmann.cu", "cgb_xtc.cu"]
-HEADERS = [CSRC / "cgb_common.cuh", CSRC.parent.parent / "include" / "pycgtool_b200.h"]
+SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_measure_fused.cu", "cgb_boltzmann.cu", "cgb_xtc.cu", "cgb_comm.cu"]
+HEADERS = [CSRC / "cgb_common.cuh", CSRC / "cgb_terms.cuh", CSRC / "cgb_measure_plan.cpp.inc",
+           CSRC.parent.parent / "include" / "pycgtool_b200.h"]
 LIBRARY = CSRC / "libpycgtool_b200.so"
 STAMP = CSRC / ".build_stamp"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl",
 ]
 
 

@@ -562,12 +562,6 @@ __global__ void __launch_bounds__(256) map_gather_kernel(const float* __restrict
 // Defaults from the sweep in profiles/ (S2, B200): 32-bead tiles, 2 stages of <= 24 KB and 3
 // consumer warps give five CTAs (15 consumer warps, ~90 KB of loads in flight) per SM.
 constexpr int kDefStageBytes = 24576, kDefStages = 2, kDefFramesPerCta = 128, kDefConsumers = 96, kDefFg = 4;
-static int g_stage_bytes = kDefStageBytes;
-static int g_stage_user = 0;  // stage size was set explicitly through cgb_map_set_tuning
-static int g_nstages = kDefStages;
-static int g_frames_per_cta = kDefFramesPerCta;
-static int g_consumers = kDefConsumers;
-static int g_fg = kDefFg;
 
 template <int FG>
 static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size_t smem, bool has_box, bool w64,
@@ -589,31 +583,12 @@ static cudaError_t launch_tiles(const MapParams& p, dim3 grid, int threads, size
 
 }  // namespace cgb
 
-extern "C" int cgb_map_set_tuning(int32_t stage_bytes, int32_t n_stages, int32_t frames_per_cta) {
-    if (stage_bytes < 0 || n_stages < 0 || n_stages > cgb::kMaxStages || frames_per_cta < 0) return CGB_EINVAL;
-    cgb::g_stage_bytes = stage_bytes ? stage_bytes : cgb::kDefStageBytes;
-    cgb::g_stage_user = stage_bytes ? 1 : 0;
-    cgb::g_nstages = n_stages ? n_stages : cgb::kDefStages;
-    cgb::g_frames_per_cta = frames_per_cta ? frames_per_cta : cgb::kDefFramesPerCta;
-    return CGB_OK;
-}
-
-// Extra benchmarking knobs: consumer threads per CTA (multiple of 32, <= 256) and frames per
-// register group (1, 2 or 4).
-extern "C" int cgb_map_set_shape(int32_t consumer_threads, int32_t frame_group) {
-    if (consumer_threads < 0 || consumer_threads > 256 || consumer_threads % 32) return CGB_EINVAL;
-    if (frame_group != 0 && frame_group != 1 && frame_group != 2 && frame_group != 4) return CGB_EINVAL;
-    cgb::g_consumers = consumer_threads ? consumer_threads : cgb::kDefConsumers;
-    cgb::g_fg = frame_group ? frame_group : cgb::kDefFg;
-    return CGB_OK;
-}
-
 extern "C" int cgb_map_tiles(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms,
                              int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles, const CgbMapEntry* entries,
                              const double* entries_w64, int32_t max_span, int32_t max_tile_entries, float* cg_xyz,
                              void* stream) {
-    return cgb_map_tiles_window(xyz, box_len, n_frames, n_atoms, 0, n_beads, tiles, n_tiles, entries, entries_w64,
-                                max_span, max_tile_entries, cg_xyz, stream);
+    return cgb_map_tiles_ex(xyz, box_len, n_frames, n_atoms, 0, n_beads, tiles, n_tiles, entries, entries_w64,
+                            max_span, max_tile_entries, cg_xyz, nullptr, stream);
 }
 
 extern "C" int cgb_copy_window_h2d(float* dst, const float* src, int64_t n_frames, int64_t n_atoms, int64_t first_atom,
@@ -631,7 +606,25 @@ extern "C" int cgb_map_tiles_window(const float* xyz, const float* box_len, int6
                                     int64_t first_atom, int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles,
                                     const CgbMapEntry* entries, const double* entries_w64, int32_t max_span,
                                     int32_t max_tile_entries, float* cg_xyz, void* stream) {
+    return cgb_map_tiles_ex(xyz, box_len, n_frames, n_atoms, first_atom, n_beads, tiles, n_tiles, entries,
+                            entries_w64, max_span, max_tile_entries, cg_xyz, nullptr, stream);
+}
+
+extern "C" int cgb_map_tiles_ex(const float* xyz, const float* box_len, int64_t n_frames, int64_t n_atoms,
+                                int64_t first_atom, int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles,
+                                const CgbMapEntry* entries, const double* entries_w64, int32_t max_span,
+                                int32_t max_tile_entries, float* cg_xyz, const CgbMapTuning* tuning, void* stream) {
     using namespace cgb;
+    // per-call tuning (no process-wide state): zero fields keep the defaults
+    const int g_stage_bytes = tuning && tuning->stage_bytes ? tuning->stage_bytes : kDefStageBytes;
+    const int g_stage_user = tuning && tuning->stage_bytes ? 1 : 0;
+    const int g_nstages = tuning && tuning->n_stages ? tuning->n_stages : kDefStages;
+    const int g_frames_per_cta = tuning && tuning->frames_per_cta ? tuning->frames_per_cta : kDefFramesPerCta;
+    const int g_consumers = tuning && tuning->consumer_threads ? tuning->consumer_threads : kDefConsumers;
+    const int g_fg = tuning && tuning->frame_group ? tuning->frame_group : kDefFg;
+    if (g_stage_bytes < 0 || g_nstages < 2 || g_nstages > kMaxStages || g_frames_per_cta < 0 || g_consumers < 32 ||
+        g_consumers > 256 || g_consumers % 32 || (g_fg != 1 && g_fg != 2 && g_fg != 4))
+        return CGB_EINVAL;
     if (n_frames < 0 || n_atoms < 0 || n_beads < 0 || n_tiles < 0 || max_span < 0 || max_tile_entries < 0 ||
         first_atom < 0)
         return CGB_EINVAL;

@@ -4,13 +4,24 @@ Frames are independent in mapping and measurement (``pycgtool/mapping.py:446-463
 and the mdtraj kernels work frame by frame); only the per-bond statistics are
 global.  So a trajectory is split into contiguous frame blocks, one per rank
 (one process per GPU), each rank maps and measures its block with no
-communication, and the packed float64 moments / histogram counts are summed
-with one NCCL all-reduce over NVLink before the epilogue.  ``torch.distributed``
-is the plumbing; with a single process every function here is a no-op.
+communication, and the packed float64 buffer ``[moments | histogram counts]`` is
+summed with ONE NCCL all-reduce over NVLink before the epilogue.
+
+The collective itself is issued by ``libpycgtool_b200.so`` (``cgb_allreduce_partials`` /
+``cgb_comm_broadcast`` on a communicator the library creates with ``cgb_comm_init``) on the
+stream the kernels run on -- no host synchronisation between measurement, reduction and
+epilogue.  ``torch.distributed`` is only the rendezvous that hands the 128-byte NCCL id to the
+other ranks, and the transport for host tensors (gloo, the CPU tests).  With a single process
+every function here is a no-op.
 """
 
+import ctypes
+
+import numpy as np
 import torch
 import torch.distributed as td
+
+_comm = None          # (handle, rank, world, device index) of the library's NCCL communicator
 
 
 def is_distributed():
@@ -38,10 +49,73 @@ def frame_shard(n_frames, rank=None, world_size=None):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def communicator():
+    """The library's NCCL communicator over all ranks (created on first use; collective)."""
+    global _comm
+    from . import _lib
+    rank, size = world()
+    dev = torch.cuda.current_device()
+    if _comm is not None and _comm[1:] == (rank, size, dev):
+        return _comm[0]
+    lib = _lib.load()
+    ident = np.zeros(_lib.COMM_ID_BYTES, dtype=np.uint8)
+    if rank == 0:
+        _lib.check(lib.cgb_comm_unique_id(ident.ctypes.data), "cgb_comm_unique_id")
+    box = [ident.tobytes()]
+    td.broadcast_object_list(box, src=0)        # rendezvous only: 128 bytes
+    ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+    handle = ctypes.c_void_p()
+    _lib.check(lib.cgb_comm_init(ident.ctypes.data, rank, size, ctypes.byref(handle)), "cgb_comm_init")
+    _comm = (handle, rank, size, dev)
+    return handle
+
+
+def destroy_communicator():
+    global _comm
+    if _comm is not None:
+        from . import _lib
+        _lib.load().cgb_comm_destroy(_comm[0])
+        _comm = None
+
+
+def allreduce_packed(tensor):
+    """In-place sum of a contiguous float64 buffer over all ranks.
+
+    Device tensors: one ``ncclAllReduce`` issued by the library on the current stream.  Host tensors
+    (the gloo tests): ``torch.distributed``."""
+    if not is_distributed():
+        return tensor
+    if tensor.is_cuda:
+        from . import _lib, device
+        if tensor.dtype != torch.float64 or not tensor.is_contiguous():
+            raise ValueError("allreduce_packed needs a contiguous float64 tensor")
+        _lib.check(_lib.load().cgb_allreduce_partials(communicator(), tensor.data_ptr(), tensor.numel(),
+                                                      device.stream_handle()), "cgb_allreduce_partials")
+    else:
+        td.all_reduce(tensor, op=td.ReduceOp.SUM)
+    return tensor
+
+
 def allreduce_sum(tensor):
-    """In-place sum over all ranks (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    """In-place sum over all ranks through ``torch.distributed`` (any dtype; host-side bookkeeping)."""
     if is_distributed():
         td.all_reduce(tensor, op=td.ReduceOp.SUM)
+    return tensor
+
+
+def broadcast_device(tensor, src=0):
+    """Broadcast a contiguous tensor from ``src`` (device tensors through the library, on the current stream)."""
+    if not is_distributed():
+        return tensor
+    if tensor.is_cuda:
+        from . import _lib, device
+        if not tensor.is_contiguous():
+            raise ValueError("broadcast_device needs a contiguous tensor")
+        _lib.check(_lib.load().cgb_comm_broadcast(communicator(), tensor.data_ptr(),
+                                                  tensor.numel() * tensor.element_size(), int(src),
+                                                  device.stream_handle()), "cgb_comm_broadcast")
+    else:
+        td.broadcast(tensor, src=src)
     return tensor
 
 

@@ -142,6 +142,7 @@ class Mapping:
         self._virtual_map_center = options.virtual_map_center
         self._masses_are_set = False
         self._plans = {}
+        self.tuning = None      # optional _lib.MapTuning, passed to every K1 launch of this object
 
         with CFG(filename) as cfg:
             for mol_name, rows in cfg.items():
@@ -187,7 +188,11 @@ class Mapping:
                 manual = self._manual_charges[mol_name]
                 if manual:
                     logger.warning("Charges assigned in mapping for molecule %s, ignoring itp charges", mol_name)
-                self._itp_section_into_mol_map(mol_map, itp[mol_name], manual)
+                try:
+                    self._itp_section_into_mol_map(mol_map, itp[mol_name], manual)
+                except KeyError:
+                    # an atom of the mapping is missing from the .itp: same message, no abort (mapping.py:178-196)
+                    logger.warning("No itp information for molecule %s found in %s", mol_name, itp.filepath)
             self._masses_are_set = True
 
     @staticmethod
@@ -482,11 +487,12 @@ class Mapping:
         if window is not None and d["n_wide"]:
             raise ValueError("an atom window cannot be combined with beads wider than a tile")
         if d["n_tiles"]:
-            _lib.check(lib.cgb_map_tiles_window(device.dptr(xyz_dev), device.dptr(box_dev), n_frames, held, first_atom,
-                                                plan.n_beads, device.dptr(d["tiles"]), d["n_tiles"],
-                                                device.dptr(d["entries"]), device.dptr(d["entries_w64"]),
-                                                d["max_span"], d["max_ent"], device.dptr(out), stream),
-                       "cgb_map_tiles_window")
+            _lib.check(lib.cgb_map_tiles_ex(device.dptr(xyz_dev), device.dptr(box_dev), n_frames, held, first_atom,
+                                            plan.n_beads, device.dptr(d["tiles"]), d["n_tiles"],
+                                            device.dptr(d["entries"]), device.dptr(d["entries_w64"]),
+                                            d["max_span"], d["max_ent"], device.dptr(out),
+                                            _lib.tuning_ptr(getattr(self, "tuning", None)), stream),
+                       "cgb_map_tiles_ex")
         if d["n_wide"]:
             _lib.check(lib.cgb_map_gather(device.dptr(xyz_dev), plan.n_atoms, device.dptr(box_dev), n_frames,
                                           plan.n_beads, device.dptr(d["bead_ptr"]), device.dptr(d["index"]),

@@ -12,8 +12,9 @@ import torch
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device  # noqa: E402
+from workloads import synth  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 
 
 STAGED = "--gather" not in sys.argv

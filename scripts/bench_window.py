@@ -11,8 +11,9 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 import pycgtool_b200.mapping as pm  # noqa: E402
-from pycgtool_b200 import Frame, Mapping, synth  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from pycgtool_b200 import Frame, Mapping  # noqa: E402
+from workloads import synth  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 
 
 def main():

@@ -12,8 +12,9 @@ import torch
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from pycgtool_b200 import Frame, Mapping, _lib, device, formats, synth  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from pycgtool_b200 import Frame, Mapping, _lib, device, formats  # noqa: E402
+from workloads import synth  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 
 
 def main():

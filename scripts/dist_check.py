@@ -17,8 +17,9 @@ import torch.distributed as td
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from pycgtool_b200 import BondSet, Frame, Mapping, dist, synth  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from pycgtool_b200 import BondSet, Frame, Mapping, dist  # noqa: E402
+from workloads import synth  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 
 
 def main():

@@ -19,9 +19,10 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from oracle import bonds as obonds, geometry as ogeom, mapping as omap  # noqa: E402
-from pycgtool_b200 import BondSet, Frame, Mapping, _lib, synth  # noqa: E402
+from pycgtool_b200 import BondSet, Frame, Mapping, _lib  # noqa: E402
+from workloads import synth  # noqa: E402
 from pycgtool_b200.bondset import HIST_BINS, HIST_RANGES  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 from tests.helpers import oracle_system  # noqa: E402
 
 REL, ANGLE_ABS, COS_ULPS = 1e-4, 2e-6, 4e-7

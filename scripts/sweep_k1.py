@@ -13,9 +13,10 @@ import torch
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from pycgtool_b200 import Mapping, _lib, synth  # noqa: E402
+from pycgtool_b200 import Mapping, _lib  # noqa: E402
+from workloads import synth  # noqa: E402
 import pycgtool_b200.mapping as pm  # noqa: E402
-from pycgtool_b200.synth import Options  # noqa: E402
+from workloads.synth import Options  # noqa: E402
 
 
 def main():

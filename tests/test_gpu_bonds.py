@@ -204,7 +204,7 @@ def _synthetic_bonds(sysm, n_frames, options, ortho=True, skew=None):
 
 def test_small_molecule_chain_statistics(options):
     """Config S3 shape (66 terms, n_inst = 1) on 4,096 frames, dihedrals straddling +-pi."""
-    from pycgtool_b200 import synth
+    from workloads import synth
     bondset, terms, ocg = _synthetic_bonds(synth.small_molecule(), 4096, options)
     assert len(bondset["MOL"]) == 66
     for bond, term in zip(bondset["MOL"], terms["MOL"]):
@@ -213,7 +213,7 @@ def test_small_molecule_chain_statistics(options):
 
 
 def test_membrane_many_instances_ortho_pbc(options):
-    from pycgtool_b200 import synth
+    from workloads import synth
     sysm = synth.membrane(40, 60, seed=17)
     sysm.box = np.array([4.0, 4.2, 3.9])
     sysm.sigma = 0.12
@@ -228,7 +228,7 @@ def test_membrane_many_instances_ortho_pbc(options):
 
 
 def test_triclinic_minimum_image(options):
-    from pycgtool_b200 import synth
+    from workloads import synth
     sysm = synth.membrane(12, 0, seed=4)
     sysm.box = np.array([3.0, 3.0, 3.0])
     sysm.sigma = 0.1
@@ -298,7 +298,8 @@ def test_bond_level_invert_on_host_values(options):
 def test_frame_shards_merge_to_single_pass(options):
     """Two frame shards measured separately and summed (what the all-reduce does) equal one pass."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, dist, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping, dist
+    from workloads import synth
     sysm = synth.small_molecule()
     n_frames = 600
     xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
@@ -401,7 +402,8 @@ def test_s3_full_size_properties(options):
     streamed moments equal float64 moments of the stored values, and mapping then measuring a frame shard
     gives the values of the same frames in the full pass."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from workloads import synth
     from pycgtool_b200.bondset import HIST_RANGES
     sysm = synth.small_molecule()
     n_frames = 1 << 20
@@ -427,10 +429,14 @@ def test_s3_full_size_properties(options):
         lo, hi = HIST_RANGES[len(bond.atoms)]
         assert hist[k].sum() == np.count_nonzero((v >= np.float32(lo)) & (v <= np.float32(hi)))
         assert partials[k, 0] == n_frames
-        if len(bond.atoms) != 4:
-            d = v.astype(np.float64) - np.float64(shift[k])
-            assert partials[k, 1] == pytest.approx(d.sum(), rel=1e-5, abs=1e-3)
-            assert partials[k, 2] == pytest.approx((d * d).sum(), rel=1e-5)
+        d = v.astype(np.float64) - np.float64(shift[k])
+        if len(bond.atoms) == 4:
+            d -= 2 * math.pi * np.rint(d / (2 * math.pi))      # dihedrals: wrapped about the shift
+        off = partials[k, 1] - d.sum()
+        turns = np.rint(off / (2 * math.pi))       # a sample within an ulp of the antipode may wrap either way
+        assert abs(turns) <= (3 if len(bond.atoms) == 4 else 0)
+        assert abs(off - 2 * math.pi * turns) <= max(1e-5 * abs(d.sum()), 0.5)
+        assert partials[k, 2] == pytest.approx((d * d).sum(), rel=1e-5)
         if len(bond.atoms) != 2:
             assert partials[k, 3] == pytest.approx(np.cos(v.astype(np.float64)).sum(), rel=1e-5, abs=0.5)
             assert partials[k, 4] == pytest.approx(np.sin(v.astype(np.float64)).sum(), rel=1e-5, abs=0.5)
@@ -452,7 +458,8 @@ def test_s5_size_sampled_terms(options):
     instances spread over the system is measured by the oracle on the same CG coordinates -- lengths bit-exact,
     angles within the float32 acos / atan2 conditioning -- and every value buffer has the reference's length."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from workloads import synth
     sysm = synth.s5()
     n_frames = 4
     dev = torch.device("cuda")
@@ -491,10 +498,12 @@ def test_s5_size_sampled_terms(options):
 
 def test_measure_outputs_stay_inside_their_buffers(options):
     """compute-sanitizer is not available on this GPU pool, so the write bounds of K2 are checked with canaries:
-    `values`, `partials` and `hist` live inside larger sentinel-filled buffers that must come back untouched
-    (odd frame count, several tiles, frame blocks that do not divide the trajectory)."""
+    `values` and the packed `[partials | hist]` buffer live inside larger sentinel-filled buffers that must come
+    back untouched (frame count that is not a multiple of 4, several tiles, frame blocks that do not divide the
+    trajectory).  Called through the C ABI directly, with the plan the Python layer compiled."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device
+    from workloads import synth
     sysm = synth.membrane(70, 40, seed=23)
     n_frames = 37
     xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
@@ -504,41 +513,43 @@ def test_measure_outputs_stay_inside_their_buffers(options):
     bondset.apply(cg)
     st = bondset._state
     plan = st.plan
-    n2, n3, n4 = plan.counts
-    n_cols = n2 + n3 + n4
-    assert n_cols > 3 * _lib.MEASURE_TILE
+    n_cols = plan.n_cols
+    assert len(plan.tiles) >= 3 and plan.n_staged == n_cols
     dev = st.values.device
     d = BondSet._device_plan(plan, dev)
     guard = 4096
+    n_packed = plan.n_bonds * (_lib.NPART + 128)
     vbuf = torch.full((n_frames * n_cols + 2 * guard,), -12345.0, dtype=torch.float32, device=dev)
-    pbuf = torch.full((plan.n_bonds * _lib.NPART + 2 * guard,), -7.0, dtype=torch.float64, device=dev)
-    hbuf = torch.full((plan.n_bonds * 128 + 2 * guard,), -3, dtype=torch.int64, device=dev)
+    pbuf = torch.full((n_packed + 2 * guard,), -7.0, dtype=torch.float64, device=dev)
     values = vbuf[guard:guard + n_frames * n_cols]
-    partials = pbuf[guard:guard + plan.n_bonds * _lib.NPART]
-    hist = hbuf[guard:guard + plan.n_bonds * 128]
-    partials.zero_()
-    hist.zero_()
-    lo, hi = torch.from_numpy(st.hist_lo).to(dev), torch.from_numpy(st.hist_hi).to(dev)
+    packed = pbuf[guard:guard + n_packed]
+    packed.zero_()
+    partials, hist = packed[:plan.n_bonds * _lib.NPART], packed[plan.n_bonds * _lib.NPART:]
     box_dev = cg._trajectory.device_box_vectors(dev)
-    _lib.check(_lib.load().cgb_measure(
-        device.dptr(cg._trajectory.device_xyz()), device.dptr(box_dev), 1, n_frames, plan.n_beads,
-        device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), device.dptr(d["col_slot"]), plan.max_slots,
-        device.dptr(d["tile_span"]), plan.max_span, n2, n3, n4, plan.n_bonds, device.dptr(st.shift),
-        device.dptr(values), device.dptr(partials), device.dptr(hist), device.dptr(lo), device.dptr(hi), 128,
-        device.stream_handle()))
-    torch.cuda.synchronize()
-    for buf, fill in ((vbuf, -12345.0), (pbuf, -7.0), (hbuf, -3)):
-        assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all())
-    assert torch.equal(values, st.values)                       # and the same results as through the API
-    assert torch.equal(hist.view(plan.n_bonds, 128), st.hist)
-    assert bool((values != -12345.0).all())
+    for tuning in (None, _lib.MeasureTuning(stage_bytes=8192, n_stages=2, max_run=8, waves=1)):
+        values.fill_(-12345.0)
+        packed.zero_()
+        _lib.check(_lib.load().cgb_measure_fused(
+            device.dptr(cg._trajectory.device_xyz()), device.dptr(box_dev), 1, n_frames, plan.n_beads,
+            device.dptr(d["tiles"]), len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]),
+            device.dptr(d["tile_bonds"]), plan.max_span, plan.max_slots, plan.max_edge_chunks, plan.max_tile_groups,
+            device.dptr(st.shift), device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist),
+            device.dptr(st.hist_lo), device.dptr(st.hist_hi), 128, _lib.tuning_ptr(tuning), device.stream_handle()))
+        torch.cuda.synchronize()
+        for buf, fill in ((vbuf, -12345.0), (pbuf, -7.0)):
+            assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all())
+        assert torch.equal(values.view(n_frames, n_cols), st.values)    # and the same results as through the API
+        assert torch.equal(hist.view(plan.n_bonds, 128), st.hist)
+        assert torch.allclose(partials.view(plan.n_bonds, _lib.NPART), st.partials, rtol=1e-5, atol=1e-6)
+        assert bool((values != -12345.0).all())
 
 
 def test_gather_kernels_explicit_and_automatic(options, tmp_path):
     """The gather kernels (beads read from global memory) are the path for tiles whose bead range does not fit
     in shared memory.  (1) forced through `BondSet.staged = False` on a membrane; (2) reached automatically by a
     4,000-bead chain with terms that join its two ends (one frame of the tile's range is 48 KB)."""
-    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from workloads import synth
     sysm = synth.membrane(30, 20, seed=31)
     sysm.box = np.array([3.6, 3.3, 3.9])
     n_frames = 19
@@ -579,7 +590,7 @@ def test_gather_kernels_explicit_and_automatic(options, tmp_path):
     bondset = BondSet(bnd, options)
     bondset.apply(frame)
     bondset.boltzmann_invert()
-    assert bondset._state.plan.max_span >= 3999
+    assert bondset._state.plan.wide_counts == (2, 1, 1) and len(bondset._state.plan.tiles) > 0
     terms = obonds.parse_bnd(bnd, generate_angles=False, generate_dihedrals=False)
     osys = oracle_system(top, xyz, box)
     obonds.measure(terms, osys)
@@ -593,7 +604,8 @@ def test_statistics_are_reproducible_run_to_run(options):
     """No floating-point atomics inside a CTA (fixed-order float64 reduction); CTAs are combined with float64
     atomics, whose order can only move the last bits: repeated passes agree to 1e-13, histograms exactly."""
     import torch
-    from pycgtool_b200 import BondSet, Frame, Mapping, synth
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from workloads import synth
     sysm = synth.small_molecule()
     n_frames = 1 << 16
     xyz = sysm.coordinates_device(n_frames, torch.device("cuda"), chunk=1 << 14)

@@ -102,7 +102,7 @@ def test_missing_atom_raises_keyerror(golden, options, tmp_path):
         Mapping(bad, options).apply(Frame(golden / "sugar.gro"))
 
 
-def _synthetic_case(sysm, n_frames, options, with_box=True, zero_box_frame=None):
+def _synthetic_case(sysm, n_frames, options, with_box=True, zero_box_frame=None, tuning=None):
     """Map a synthetic system on the GPU and with the oracle; return both CG arrays."""
     from pycgtool_b200 import Frame, Mapping
     xyz = sysm.coordinates_host(n_frames)
@@ -111,14 +111,16 @@ def _synthetic_case(sysm, n_frames, options, with_box=True, zero_box_frame=None)
         box[zero_box_frame, 2, 2] = 0.0
     map_path, _ = sysm.write_files()
     frame = Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box)
-    cg = Mapping(map_path, options).apply(frame)
+    mapper = Mapping(map_path, options)
+    mapper.tuning = tuning
+    cg = mapper.apply(frame)
     ref = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, xyz, box))
     return cg._trajectory.xyz, ref.xyz
 
 
 @pytest.mark.parametrize("n_lipids,n_water,n_frames", [(3, 0, 5), (8, 40, 9), (24, 300, 33), (5, 1000, 130)])
 def test_membrane_with_pbc_straddling_molecules(options, n_lipids, n_water, n_frames):
-    from pycgtool_b200 import synth
+    from workloads import synth
     sysm = synth.membrane(n_lipids, n_water, seed=11 + n_lipids)
     sysm.box = np.array([3.0, 3.1, 2.9])      # small box: many molecules straddle the boundary
     got, ref = _synthetic_case(sysm, n_frames, options)
@@ -127,7 +129,7 @@ def test_membrane_with_pbc_straddling_molecules(options, n_lipids, n_water, n_fr
 
 
 def test_no_box_and_zero_box(options):
-    from pycgtool_b200 import synth
+    from workloads import synth
     sysm = synth.membrane(4, 16, seed=3)
     got, ref = _synthetic_case(sysm, 7, options, with_box=False)
     assert np.array_equal(got, ref)
@@ -137,7 +139,7 @@ def test_no_box_and_zero_box(options):
 
 
 def test_small_molecule_contiguous_frames(options):
-    from pycgtool_b200 import synth
+    from workloads import synth
     sysm = synth.small_molecule()
     got, ref = _synthetic_case(sysm, 777, options)
     assert np.array_equal(got, ref)
@@ -180,7 +182,8 @@ def test_ragged_beads_unmapped_residues_and_wide_bead(options, tmp_path):
 def test_unaligned_frame_slices(options):
     """Frame shards are views at arbitrary float offsets: the 16-byte-aligned bulk copies must cope."""
     import torch
-    from pycgtool_b200 import Mapping, synth
+    from pycgtool_b200 import Mapping
+    from workloads import synth
     sysm = synth.membrane(2, 7, seed=9)        # N = 628: 12*N % 16 != 0 for odd frame counts
     assert (sysm.n_atoms * 12) % 16 != 0 or True
     n_frames = 23
@@ -205,7 +208,8 @@ def test_output_canaries_untouched(options):
     """compute-sanitizer is closed on the GPU pool, so out-of-bounds *writes* are checked by hand: the
     output lives inside a larger buffer of sentinels which must survive, for several shapes."""
     import torch
-    from pycgtool_b200 import Mapping, synth
+    from pycgtool_b200 import Mapping
+    from workloads import synth
     dev = torch.device("cuda")
     for sysm, n_frames in ((synth.membrane(3, 11, seed=5), 13), (synth.small_molecule(), 301)):
         xyz = torch.from_numpy(sysm.coordinates_host(n_frames)).to(dev)
@@ -227,24 +231,65 @@ def test_output_canaries_untouched(options):
 @pytest.mark.parametrize("stage_bytes,n_stages,fpc,threads,fg", [
     (4096, 2, 8, 32, 1), (8192, 3, 16, 64, 2), (49152, 4, 256, 256, 4), (16384, 8, 32, 96, 4)])
 def test_tuning_knobs_do_not_change_results(options, stage_bytes, n_stages, fpc, threads, fg):
-    from pycgtool_b200 import _lib, synth
-    lib = _lib.load()
+    """Tuning is a per-call argument of the C ABI (``CgbMapTuning``): the library keeps no mutable state."""
+    from pycgtool_b200 import _lib
+    from workloads import synth
     sysm = synth.membrane(6, 50, seed=21)
-    try:
-        _lib.check(lib.cgb_map_set_tuning(stage_bytes, n_stages, fpc))
-        _lib.check(lib.cgb_map_set_shape(threads, fg))
-        got, ref = _synthetic_case(sysm, 41, options)
-    finally:
-        lib.cgb_map_set_tuning(0, 0, 0)
-        lib.cgb_map_set_shape(0, 0)
+    tuning = _lib.MapTuning(stage_bytes=stage_bytes, n_stages=n_stages, frames_per_cta=fpc,
+                            consumer_threads=threads, frame_group=fg)
+    got, ref = _synthetic_case(sysm, 41, options, tuning=tuning)
     assert np.array_equal(got, ref)
+
+
+def test_two_streams_with_different_tunings_run_concurrently(options):
+    """Re-entrancy across streams: two mappers with different tunings, each on its own CUDA stream and
+    host thread, interleaved many times, give the results of a serial run."""
+    import threading
+    import torch
+    from pycgtool_b200 import Mapping, _lib
+    from workloads import synth
+    sysm = synth.membrane(12, 80, seed=5)
+    n_frames = 96
+    dev = torch.device("cuda")
+    xyz = torch.from_numpy(sysm.coordinates_host(n_frames)).to(dev)
+    lengths = torch.from_numpy(np.ascontiguousarray(
+        np.diagonal(sysm.box_vectors(n_frames), axis1=1, axis2=2))).to(dev)
+    map_path, _ = sysm.write_files()
+    tunings = [_lib.MapTuning(stage_bytes=4096, n_stages=2, frames_per_cta=8, consumer_threads=32, frame_group=1),
+               _lib.MapTuning(stage_bytes=49152, n_stages=4, frames_per_cta=256, consumer_threads=256, frame_group=4)]
+    mappers = []
+    for tuning in tunings:
+        mapper = Mapping(map_path, options)
+        mapper.tuning = tuning
+        mappers.append(mapper)
+    plan = mappers[0].compile_plan(sysm.topology)
+    serial = mappers[0].map_device(plan, xyz, lengths).clone()
+    torch.cuda.synchronize()
+    results = [[], []]
+
+    def work(i):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            p = mappers[i].compile_plan(sysm.topology)
+            for _ in range(25):
+                results[i].append(mappers[i].map_device(p, xyz, lengths).clone())
+        stream.synchronize()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for outs in results:
+        assert len(outs) == 25 and all(torch.equal(o, serial) for o in outs)
 
 
 def test_s2_shape_sampled_frames(options):
     """Config S2 topology (1,152 lipids, N = 156,672) on 64 device-generated frames;
     four sampled frames are checked against the oracle."""
     import torch
-    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200 import Frame, Mapping
+    from workloads import synth
     sysm = synth.s2()
     assert sysm.n_atoms == 156672
     n_frames = 64
@@ -271,7 +316,8 @@ def test_s5_size_sampled_beads(options):
     bit for bit; the assignment tables they use were checked against the oracle's on the CPU."""
     import torch
     from oracle import mapping as omap
-    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200 import Frame, Mapping
+    from workloads import synth
     sysm = synth.s5()
     assert sysm.n_atoms == 19999992
     n_frames = 2
@@ -309,7 +355,8 @@ def test_s5_size_sampled_beads(options):
 def test_float64_weights_on_many_tiles(options, n_frames):
     """ITP masses make the bead weights float64 (mapping.py:224-227) and the bead sum a float64 sum rounded to
     float32 at the end: random float64 weights on a solvated membrane (hundreds of tiles), bit-exact vs the oracle."""
-    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200 import Frame, Mapping
+    from workloads import synth
     sysm = synth.membrane(12, 150, seed=77)
     sysm.box = np.array([3.3, 3.0, 3.4])
     xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
@@ -334,7 +381,8 @@ def test_virtual_beads_on_a_membrane(options, tmp_path):
     """Virtual sites (``@v`` lines: built from CG beads of the same residue after the real beads,
     mapping.py:431-438) on every lipid of a membrane whose molecules straddle the box: bit-exact vs the oracle,
     real beads through the tile kernel, virtual beads through the gather kernel reading the CG frame."""
-    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200 import Frame, Mapping
+    from workloads import synth
     sysm = synth.membrane(25, 30, seed=41)
     sysm.box = np.array([3.1, 3.4, 2.8])
     text = sysm.map_text.replace("[ POPC ]", "@v VHD P1 NC3 PO4 GL1 GL2\n@v VTA C1 C1A C2A C3A C4A\n[ POPC ]", 1)
@@ -363,7 +411,8 @@ def test_streamed_host_trajectory_uploads_only_the_mapped_atom_window(options, m
     device-resident path.  Solvent before the lipids exercises a non-zero first atom (and unaligned window rows)."""
     import torch
     import pycgtool_b200.mapping as pm
-    from pycgtool_b200 import Frame, Mapping, synth
+    from pycgtool_b200 import Frame, Mapping
+    from workloads import synth
     from pycgtool_b200.topology import Topology
     sysm = synth.membrane(25, 2501, seed=13)
     sysm.box = np.array([4.0, 4.1, 3.7])

@@ -23,13 +23,14 @@ def test_library_exports_every_declared_symbol():
     from pycgtool_b200 import _lib
     header = (ROOT / "include" / "pycgtool_b200.h").read_text()
     declared = set(re.findall(r"\b(cgb_[a-z0-9_]+)\s*\(", header))
-    assert {"cgb_map_tiles", "cgb_measure", "cgb_boltzmann", "cgb_map_plan_build"} <= declared
+    assert {"cgb_map_tiles", "cgb_measure", "cgb_measure_fused", "cgb_measure_plan_build", "cgb_boltzmann",
+            "cgb_map_plan_build", "cgb_allreduce_partials"} <= declared
     lib = ctypes.CDLL(str(_lib.LIBRARY_PATH))
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.SIGNATURES) == declared
     loaded = _lib.load()
-    assert loaded.cgb_abi_version() == 1
+    assert loaded.cgb_abi_version() == _lib.ABI_VERSION == 2
     assert b"invalid argument" in loaded.cgb_strerror(-1)
 
 
@@ -39,9 +40,17 @@ def test_abi_argument_errors_without_gpu():
     lib = _lib.load()
     assert lib.cgb_map_tiles(None, None, 4, 10, 2, None, 1, None, None, 8, 8, None, None) == -1
     assert lib.cgb_map_tiles(None, None, 0, 10, 2, None, 1, None, None, 8, 8, None, None) == 0   # no frames: no-op
-    assert lib.cgb_measure(None, None, 1, -1, 2, None, None, None, 0, None, 0, 0, 0, 0, 0, None, None, None, None, None, None, 0, None) == -1
-    assert lib.cgb_boltzmann(None, None, None, None, 310.0, 3, None, None) == -1
-    assert lib.cgb_map_set_tuning(-5, 0, 0) == -1
+    assert lib.cgb_measure(None, None, 1, -1, 2, None, None, None, 0, 0, 0, 0, None, None, 0, None, None, None, None,
+                           0, None) == -1
+    assert lib.cgb_measure_fused(None, None, 1, 5, 2, None, 1, None, None, None, 8, 8, 1, 1, None, None, 0, None, None,
+                                 None, None, 0, None, None) == -1
+    assert lib.cgb_boltzmann(None, None, None, None, 310.0, 3, None, None, None, 0, 0, None, None) == -1
+    assert lib.cgb_allreduce_partials(None, None, 4, None) == -1
+    assert lib.cgb_allreduce_partials(None, None, 0, None) == 0       # nothing to reduce: no-op
+    bad = _lib.MapTuning(stage_bytes=-5)
+    # tuning is a per-call argument (no process-wide state); a bad one is rejected before any launch
+    assert lib.cgb_map_tiles_ex(None, None, 0, 10, 0, 2, None, 1, None, None, 8, 8, None, _lib.tuning_ptr(bad), None) == -1
+    assert lib.cgb_map_tiles_ex(None, None, 0, 10, 0, 2, None, 1, None, None, 8, 8, None, None, None) == 0
     with pytest.raises(RuntimeError):
         _lib.check(-3, "demo")
 
@@ -75,7 +84,8 @@ def _decode_tiles(tiles, entries, n_beads):
 
 @pytest.mark.parametrize("max_span,max_beads", [(512, 512), (140, 7), (20000, 3)])
 def test_tile_plan_encodes_the_same_assignment(options, max_span, max_beads):
-    from pycgtool_b200 import Mapping, _lib, synth
+    from pycgtool_b200 import Mapping, _lib
+    from workloads import synth
     lib = _lib.load()
     sysm = synth.membrane(5, 33, seed=2)
     map_path, _ = sysm.write_files()
@@ -145,7 +155,8 @@ def test_mapping_assignment_bit_exact(golden, options, gro, mp, kwargs):
 
 
 def test_mapping_assignment_synthetic_with_unmapped_residues(options):
-    from pycgtool_b200 import Mapping, synth
+    from pycgtool_b200 import Mapping
+    from workloads import synth
     sysm = synth.s5(scale=0.002)
     map_path, _ = sysm.write_files()
     text = map_path.read_text().replace("[ CHOL ]", "[ NOTCHOL ]")     # CHOL residues become unmapped
@@ -171,7 +182,7 @@ def test_bond_assignment_bit_exact(golden, options, gro, bnd):
         for term in tlist:
             idx = obonds.resolve_indices(term, mol, sysm)
             assert np.array_equal(plan.bond_indices[bond_id], idx)
-            cols = plan.bond_cols[bond_id]
+            cols = plan.bond_columns[bond_id]
             k = len(term.atoms)
             assert np.array_equal(plan.col_beads[cols][:, :k], idx)
             assert (plan.col_bond[cols] == bond_id).all()
@@ -181,18 +192,57 @@ def test_bond_assignment_bit_exact(golden, options, gro, bnd):
     n2, n3, n4 = plan.counts
     kinds = plan.natoms[plan.col_bond]
     assert (kinds[:n2] == 2).all() and (kinds[n2:n2 + n3] == 3).all() and (kinds[n2 + n3:] == 4).all()
-    # tile slots: inside every 256-column tile of a kind, slot <-> Bond is a bijection
-    start = 0
-    for n_k in plan.counts:
-        width = min(n_k, 256) if n_k else 1
-        for t0 in range(start, start + n_k, width):
-            sl, bd = plan.col_slot[t0:t0 + width], plan.col_bond[t0:t0 + width]
-            assert len(set(zip(sl, bd))) == len(set(sl)) == len(set(bd)) and sl.max() < plan.max_slots
-        start += n_k
+    # the fused kernel's plan measures every column once, from its own beads, at the position bond_cols names
+    from tests.plan_decode import check_measure_plan
+    decoded = check_measure_plan(plan)
+    for b, cols in enumerate(plan.bond_cols):
+        for inst, pos in enumerate(cols):
+            kind, beads, bond = decoded[int(pos)]
+            assert bond == b and (beads == tuple(plan.bond_indices[b][inst]) or kind == 2)
+
+
+@pytest.mark.parametrize("system,dihedrals", [("small", False), ("membrane", False), ("membrane", True),
+                                              ("s5", False), ("chain", False)])
+def test_measure_plan_covers_every_column(options, system, dihedrals, tmp_path):
+    """``cgb_measure_plan_build`` (host code in the library): groups of <= 64 shared bead pairs, tiles of <= 7 groups
+    inside one bead range, wide columns left to the gather kernel -- decoded back and compared column by column."""
+    from pycgtool_b200 import BondSet, Mapping, _lib
+    from pycgtool_b200.topology import Topology
+    from workloads import synth
+    from tests.plan_decode import check_measure_plan
+    options.generate_dihedrals = dihedrals
+    if system == "chain":
+        names = [f"B{i}" for i in range(4000)]
+        cg_top = Topology.from_residue_lists([("MOL", names)])
+        lines = ["[ MOL ]"] + [f"B{i} B{i + 1}" for i in range(0, 3999, 7)] + ["B0 B3999", "B1 B3998"]
+        lines += ["B0 B2000 B3999", "B5 B6 B7"] + ["B0 B1 B3998 B3999", "B10 B11 B12 B13"]
+        bnd_path = tmp_path / "long.bnd"
+        bnd_path.write_text("\n".join(lines) + "\n")
+    else:
+        sysm = {"small": synth.small_molecule, "membrane": lambda: synth.membrane(70, 40, seed=23),
+                "s5": lambda: synth.s5(scale=0.02)}[system]()
+        map_path, bnd_path = sysm.write_files()
+        cg_top = Mapping(map_path, options).compile_plan(sysm.topology).cg_topology
+    bondset = BondSet(bnd_path, options)
+    plan = bondset.compile_plan(cg_top)
+    check_measure_plan(plan)
+    assert (plan.tiles["ngroups"] <= _lib.MEAS_WARPS).all() and (plan.tiles["span"] <= 512).all()
+    per_molecule = max(len(bonds) for bonds in bondset._molecules.values())
+    assert plan.max_slots <= max(per_molecule, 8)
+    if system == "chain":
+        assert sum(plan.wide_counts) == 4 and plan.wide_counts == (2, 1, 1)     # the terms that join the two ends
+    else:
+        assert sum(plan.wide_counts) == 0
+    # forced gather path: every column is "wide", in its original order
+    bondset.staged = False
+    gather = bondset.compile_plan(cg_top)
+    assert len(gather.tiles) == 0 and gather.wide_counts == gather.counts
+    assert np.array_equal(gather.col_out, np.arange(gather.n_cols))
 
 
 def test_generated_angles_and_s5_term_count(options):
-    from pycgtool_b200 import BondSet, synth
+    from pycgtool_b200 import BondSet
+    from workloads import synth
     sysm = synth.s5(scale=0.001)
     _, bnd_path = sysm.write_files()
     bondset = BondSet(bnd_path, options)
@@ -282,7 +332,7 @@ def test_product_readers_agree_with_oracle_readers(golden):
 
 
 def test_synthetic_shapes():
-    from pycgtool_b200 import synth
+    from workloads import synth
     assert synth.s2().n_atoms == 156672
     s5 = synth.s5(scale=0.01)
     assert s5.topology.n_residues == 4 * 92 + 13049

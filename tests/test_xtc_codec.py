@@ -31,7 +31,8 @@ def test_reference_kat_first_atom_of_water_xtc(golden):
 
 @pytest.mark.parametrize("n_lipids,n_water,frames,precision", [(4, 30, 7, 1000.0), (1, 0, 3, 500.0), (0, 50, 5, 100.0)])
 def test_encode_decode_round_trip(tmp_path, n_lipids, n_water, frames, precision):
-    from pycgtool_b200 import formats, synth
+    from pycgtool_b200 import formats
+    from workloads import synth
     sysm = synth.membrane(max(n_lipids, 1), n_water, seed=3) if n_lipids else synth.membrane(1, n_water, seed=4)
     x, box = sysm.coordinates_host(frames), sysm.box_vectors(frames)
     image = formats.encode_xtc(x, box, precision=precision)
@@ -93,7 +94,8 @@ def test_gpu_decoder_matches_host_on_reference_fixtures(golden, name):
 @pytest.mark.gpu
 def test_gpu_decoder_on_synthetic_membrane_and_pipeline(tmp_path, options):
     """Compressed file -> GPU decode -> mapping equals host decode -> mapping, bit for bit."""
-    from pycgtool_b200 import Frame, Mapping, formats, synth
+    from pycgtool_b200 import Frame, Mapping, formats
+    from workloads import synth
     sysm = synth.membrane(6, 200, seed=8)
     frames = 37
     x, box = sysm.coordinates_host(frames), sysm.box_vectors(frames)
@@ -114,7 +116,8 @@ def test_pipelined_upload_in_many_blocks(tmp_path):
     """Blocks of a few frames (upload on the copy stream, decode on the compute stream) give the same floats,
     and the per-block hook sees every frame exactly once, in order."""
     import torch
-    from pycgtool_b200 import formats, synth
+    from pycgtool_b200 import formats
+    from workloads import synth
     sysm = synth.membrane(4, 60, seed=3)
     frames = 53
     image = formats.encode_xtc(sysm.coordinates_host(frames), sysm.box_vectors(frames), precision=1000.0)

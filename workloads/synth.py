@@ -16,7 +16,7 @@ import tempfile
 
 import numpy as np
 
-from .topology import Topology
+from pycgtool_b200.topology import Topology
 
 MARTINI_12 = ["NC3", "PO4", "GL1", "GL2", "C1A", "C2A", "C3A", "C4A", "C1B", "C2B", "C3B", "C4B"]
 MARTINI_8 = ["NC3", "PO4", "GL1", "GL2", "C1A", "C2A", "C1B", "C2B"]

@@ -175,12 +175,16 @@ int cgb_map_tiles_ex(const float* xyz, const float* box_len, int64_t n_frames, i
 #define CGB_MEAS_WARPS 7          /* consumer warps per CTA = groups per tile at most                    */
 #define CGB_MEAS_CHUNKS 4         /* 32-lane chunks per group                                            */
 #define CGB_MEAS_EDGE_CHUNKS 2    /* of which at most this many hold edges (bead pairs)                  */
+/* Shape of every group of a plan: the kind of each of its four chunks, fixed at compile time in the kernel. */
+#define CGB_SHAPE_EAD 0           /* [edges | angles | dihedrals | unused]: <= 32 of each                 */
+#define CGB_SHAPE_EEAA 1          /* [edges | edges | angles | angles]: <= 64 of each, no dihedrals        */
 
 typedef struct CgbMeasTile {      /* 32 bytes: the work of one CTA */
     int32_t bead0, span;          /* contiguous bead range staged per frame                              */
     int32_t group0, ngroups;      /* its groups                                                          */
     int32_t slot0, nslots;        /* tile_bonds[slot0 .. slot0 + nslots): Bond of every tile-local slot  */
-    int32_t reserved[2];
+    int32_t list0, nlist;         /* tile_lists[list0 ..): uint16 slot_ptr[nslots + 1], then nlist lane-roles
+                                     (chunk * 224 + group-in-tile * 32 + lane) grouped by slot            */
 } CgbMeasTile;
 
 typedef struct CgbMeasGroup {     /* 32 bytes: the work of one warp */
@@ -201,42 +205,55 @@ typedef struct CgbMeasLane {
 } CgbMeasLane;
 
 typedef struct CgbMeasPlanInfo {
-    int64_t n_tiles, n_groups, n_tile_bonds;
+    int64_t n_tiles, n_groups, n_tile_bonds, n_tile_lists;
     int64_t n_wide;               /* columns whose beads are too far apart for a tile (gather kernel)     */
     int64_t n_staged;             /* columns of the fused kernel: positions [0, n_staged) of the values row */
     int32_t max_span, max_slots, max_edge_chunks, max_tile_groups;
 } CgbMeasPlanInfo;
 
-/* Limits to compile a plan with, for a histogram of n_bins bins (with_hist = 0: no histogram). */
-int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t* max_span, int32_t* max_slots);
+/* Limits to compile a plan with, for a histogram of n_bins bins (with_hist = 0: no histogram): want_slots = the
+ * Bonds the caller would like one tile to hold (those of its largest molecule); max_slots <= want_slots and
+ * max_span, the widest bead range, are what fits the shared memory of a CTA together. */
+int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t want_slots, int32_t* max_span, int32_t* max_slots);
 
-/* Host-side plan compiler (all pointers HOST memory).  Pass 1 sizes the arrays; pass 2 fills them:
- * tiles[n_tiles], groups[n_groups], lanes[n_groups][CGB_MEAS_CHUNKS][32], tile_bonds[n_tile_bonds],
+/* Host-side plan compiler (all pointers HOST memory).  shape: CGB_SHAPE_EAD, or CGB_SHAPE_EEAA when n4 == 0.
+ * Pass 1 sizes the arrays; pass 2 fills them: tiles[n_tiles], groups[n_groups],
+ * lanes[n_groups][CGB_MEAS_CHUNKS][32], tile_bonds[n_tile_bonds], tile_lists[n_tile_lists] (uint16),
  * col_out[M] (position of every column in the values row; wide columns follow the staged ones, in kind
  * order) and wide_cols[n_wide] (the columns left to cgb_measure). */
 int cgb_measure_plan_size(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
-                          int64_t n_beads, int32_t max_span, int32_t max_slots, CgbMeasPlanInfo* info);
+                          int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape,
+                          CgbMeasPlanInfo* info);
 int cgb_measure_plan_build(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
-                           int64_t n_beads, int32_t max_span, int32_t max_slots, CgbMeasTile* tiles,
-                           CgbMeasGroup* groups, CgbMeasLane* lanes, int32_t* tile_bonds, int32_t* col_out,
-                           int64_t* wide_cols);
+                           int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape, CgbMeasTile* tiles,
+                           CgbMeasGroup* groups, CgbMeasLane* lanes, int32_t* tile_bonds, uint16_t* tile_lists,
+                           int32_t* col_out, int64_t* wide_cols);
 
 /* Benchmarking knobs of K2, passed per call (NULL or a zero field keeps the default). */
 typedef struct CgbMeasureTuning {
     int32_t stage_bytes;   /* bytes per pipeline stage                                                    */
     int32_t n_stages;      /* pipeline depth (2..4)                                                       */
     int32_t max_run;       /* frames a lane accumulates in float32 before its CTA reduces in float64      */
-    int32_t waves;         /* CTAs per resident slot when the frames provide the parallelism              */
+    int32_t ctas_per_sm;   /* persistent CTAs per SM (1 or 2)                                             */
     int32_t reserved[4];
 } CgbMeasureTuning;
 
-/* K2: one launch for all columns of the plan (device copies of its arrays). */
+/* K2: one launch of persistent CTAs for all columns of the plan (device copies of its arrays).  The work items
+ * (tile, block of frames) are dealt to the CTAs in equal contiguous shares. */
 int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
                       const CgbMeasTile* tiles, int64_t n_tiles, const CgbMeasGroup* groups,
-                      const CgbMeasLane* lanes, const int32_t* tile_bonds, int32_t max_span, int32_t max_slots,
-                      int32_t max_edge_chunks, int32_t max_tile_groups, const float* shift, float* values,
-                      int64_t row_stride, double* partials, double* hist, const float* hist_lo,
-                      const float* hist_hi, int32_t n_bins, const CgbMeasureTuning* tuning, void* stream);
+                      const CgbMeasLane* lanes, const int32_t* tile_bonds, const uint16_t* tile_lists,
+                      int32_t shape, int32_t max_span, int32_t max_slots, int32_t max_edge_chunks,
+                      int32_t max_tile_groups, const float* shift, float* values, int64_t row_stride,
+                      double* partials, double* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
+                      const CgbMeasureTuning* tuning, void* stream);
+
+/* Host only (no CUDA call): the launch configuration cgb_measure_fused would choose on a device with sm_count
+ * SMs.  out: int64[8] = {CTAs, shared-memory bytes per CTA, frames per stage, pipeline stages, frame blocks per
+ * segment, frame blocks per tile, 1 if the one tile is the whole frame, 0}.  CGB_ETOOBIG when it does not fit. */
+int cgb_measure_fused_config(int64_t n_frames, int64_t n_beads, int64_t n_tiles, int32_t max_span, int32_t max_slots,
+                             int32_t max_edge_chunks, int32_t max_tile_groups, int32_t n_bins, int with_hist,
+                             const CgbMeasureTuning* tuning, int32_t sm_count, int64_t* out);
 
 /* ---- gather kernels: columns straight from global memory (wide columns, or callers without a plan) ----
  * col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one

@@ -16,6 +16,7 @@ MEASURE_TILE = 224  # CGB_MEASURE_TILE
 MEAS_WARPS = 7  # CGB_MEAS_WARPS
 MEAS_CHUNKS = 4  # CGB_MEAS_CHUNKS
 MEAS_EDGE_CHUNKS = 2  # CGB_MEAS_EDGE_CHUNKS
+SHAPE_EAD, SHAPE_EEAA = 0, 1  # CGB_SHAPE_*: [edges | angles | dihedrals | -] / [edges | edges | angles | angles]
 COMM_ID_BYTES = 128  # CGB_COMM_ID_BYTES
 ABI_VERSION = 2  # CGB_ABI_VERSION
 
@@ -37,6 +38,7 @@ class MeasPlanInfo(ctypes.Structure):
         ("n_tiles", ctypes.c_int64),
         ("n_groups", ctypes.c_int64),
         ("n_tile_bonds", ctypes.c_int64),
+        ("n_tile_lists", ctypes.c_int64),
         ("n_wide", ctypes.c_int64),
         ("n_staged", ctypes.c_int64),
         ("max_span", ctypes.c_int32),
@@ -64,14 +66,14 @@ class MeasureTuning(ctypes.Structure):
         ("stage_bytes", ctypes.c_int32),
         ("n_stages", ctypes.c_int32),
         ("max_run", ctypes.c_int32),
-        ("waves", ctypes.c_int32),
+        ("ctas_per_sm", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 4),
     ]
 
 
 #: numpy dtypes of the plan structs of include/pycgtool_b200.h (CgbMeasTile, CgbMeasGroup, CgbMeasLane)
 MEAS_TILE_DTYPE = [("bead0", "<i4"), ("span", "<i4"), ("group0", "<i4"), ("ngroups", "<i4"),
-                   ("slot0", "<i4"), ("nslots", "<i4"), ("reserved", "<i4", (2,))]
+                   ("slot0", "<i4"), ("nslots", "<i4"), ("list0", "<i4"), ("nlist", "<i4")]
 MEAS_GROUP_DTYPE = [("kind", "u1", (4,)), ("nlanes", "u1", (4,)), ("nemit", "u1", (4,)),
                     ("vcol0", "<i4", (4,)), ("reserved", "<i4")]
 MEAS_LANE_DTYPE = [("ref", "<u4"), ("slot", "<i4")]
@@ -105,11 +107,13 @@ SIGNATURES = {
     "cgb_copy_window_h2d": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "cgb_map_tiles_ex": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "cgb_measure_plan_limits": (_int, [_i32, _int, _vp, _vp]),
-    "cgb_measure_plan_size": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
-    "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cgb_measure_fused": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
-                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "cgb_measure_plan_limits": (_int, [_i32, _int, _i32, _vp, _vp]),
+    "cgb_measure_plan_size": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp]),
+    "cgb_measure_fused": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                 _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "cgb_measure_fused_config": (_int, [_i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _int, _vp, _i32, _vp]),
     "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i64, _i64,
                            _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cgb_measure_shift": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),

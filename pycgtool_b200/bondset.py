@@ -153,7 +153,8 @@ class MeasurePlan:
         self.bond_first = None        # int32 (n_bonds, 4): beads of each bond's first instance
         self.natoms_measured = None   # int32 (n_bonds,): natoms, 0 for a bond without instances
         # fused kernel (cgb_measure_fused): structured arrays mirroring include/pycgtool_b200.h
-        self.tiles = self.groups = self.lanes = self.tile_bonds = None
+        self.tiles = self.groups = self.lanes = self.tile_bonds = self.tile_lists = None
+        self.shape = _lib.SHAPE_EAD   # kinds of the four chunks of every group (compile-time in the kernel)
         self.n_staged = 0             # columns [0, n_staged) of the values row come from the fused kernel
         self.max_span = self.max_slots = self.max_edge_chunks = self.max_tile_groups = 0
         self.col_out = None           # int32 (M,): position of every column in the values row
@@ -255,7 +256,7 @@ class _MeasureState:
                 if n_cols and self.n_frames:
                     _lib.check(lib.cgb_circular_pass2(device.dptr(self.values), self.n_frames, n_cols,
                                                       device.dptr(d["col_bond_by_pos"]), n_cols,
-                                                      device.dptr(self.partials), device.dptr(out[:, 4:]),
+                                                      device.dptr(self.partials), out.data_ptr() + 4 * 8,
                                                       _lib.NOUT, stream), "cgb_circular_pass2")
                 if dist.is_distributed():
                     wrapped = self.partials[:, 5].contiguous()
@@ -551,8 +552,11 @@ class BondSet:
         n2, n3, n4 = plan.counts
         n_cols = n2 + n3 + n4
         nbins = int(self.histogram_bins)
+        # Bonds per tile: what the largest molecule needs (a tile then never mixes molecule types, which keeps
+        # its shared-memory histograms small), within what fits
+        per_molecule = max([len(bonds) for bonds in self._molecules.values()] + [8])
         max_span, max_slots = ctypes.c_int32(), ctypes.c_int32()
-        _lib.check(lib.cgb_measure_plan_limits(nbins, 1, ctypes.byref(max_span), ctypes.byref(max_slots)),
+        _lib.check(lib.cgb_measure_plan_limits(nbins, 1, per_molecule, ctypes.byref(max_span), ctypes.byref(max_slots)),
                    "cgb_measure_plan_limits")
         plan.col_out = np.arange(n_cols, dtype=np.int32)
         wide = np.arange(n_cols, dtype=np.int64)
@@ -560,23 +564,24 @@ class BondSet:
         plan.groups = np.zeros(0, dtype=_lib.MEAS_GROUP_DTYPE)
         plan.lanes = np.zeros(0, dtype=_lib.MEAS_LANE_DTYPE)
         plan.tile_bonds = np.zeros(0, dtype=np.int32)
+        plan.tile_lists = np.zeros(0, dtype=np.uint16)
+        plan.shape = _lib.SHAPE_EAD if n4 else _lib.SHAPE_EEAA
         if self.staged and n_cols:
             info = _lib.MeasPlanInfo()
-            # Bonds per tile: what the largest molecule needs (a tile then never mixes molecule types, which keeps
-            # its shared-memory histograms small), within what fits
-            per_molecule = max([len(bonds) for bonds in self._molecules.values()] + [1])
-            slots = min(max_slots.value, max(per_molecule, 8))
+            slots = max_slots.value
             args = (_lib.ptr(plan.col_beads), _lib.ptr(plan.col_bond), n2, n3, n4, plan.n_beads,
-                    max_span.value, slots)
+                    max_span.value, slots, plan.shape)
             _lib.check(lib.cgb_measure_plan_size(*args, ctypes.byref(info)), "cgb_measure_plan_size")
             plan.tiles = np.zeros(info.n_tiles, dtype=_lib.MEAS_TILE_DTYPE)
             plan.groups = np.zeros(info.n_groups, dtype=_lib.MEAS_GROUP_DTYPE)
             plan.lanes = np.zeros(info.n_groups * _lib.MEAS_CHUNKS * 32, dtype=_lib.MEAS_LANE_DTYPE)
             plan.tile_bonds = np.zeros(info.n_tile_bonds, dtype=np.int32)
+            plan.tile_lists = np.zeros(info.n_tile_lists, dtype=np.uint16)
             wide = np.zeros(info.n_wide, dtype=np.int64)
             _lib.check(lib.cgb_measure_plan_build(*args, _lib.ptr(plan.tiles), _lib.ptr(plan.groups),
                                                   _lib.ptr(plan.lanes), _lib.ptr(plan.tile_bonds),
-                                                  _lib.ptr(plan.col_out), _lib.ptr(wide)), "cgb_measure_plan_build")
+                                                  _lib.ptr(plan.tile_lists), _lib.ptr(plan.col_out), _lib.ptr(wide)),
+                       "cgb_measure_plan_build")
             plan.n_staged = int(info.n_staged)
             plan.max_span, plan.max_slots = int(info.max_span), int(info.max_slots)
             plan.max_edge_chunks, plan.max_tile_groups = int(info.max_edge_chunks), int(info.max_tile_groups)
@@ -636,6 +641,7 @@ class BondSet:
                 "groups": device.to_device(plan.groups.view(np.int32), dev),
                 "lanes": device.to_device(plan.lanes.view(np.int32), dev),
                 "tile_bonds": device.to_device(plan.tile_bonds, dev),
+                "tile_lists": device.to_device(plan.tile_lists.view(np.int16), dev),
                 "wide_beads": device.to_device(plan.wide_beads, dev),
                 "wide_bond": device.to_device(plan.wide_bond, dev),
                 "wide_slot": device.to_device(plan.wide_slot, dev),
@@ -662,7 +668,8 @@ class BondSet:
             _lib.check(lib.cgb_measure_fused(
                 device.dptr(xyz), device.dptr(box_dev), ortho, n_frames, plan.n_beads, device.dptr(d["tiles"]),
                 len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]), device.dptr(d["tile_bonds"]),
-                plan.max_span, plan.max_slots, plan.max_edge_chunks, plan.max_tile_groups, device.dptr(shift),
+                device.dptr(d["tile_lists"]), plan.shape, plan.max_span, plan.max_slots, plan.max_edge_chunks,
+                plan.max_tile_groups, device.dptr(shift),
                 device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist), device.dptr(hist_lo),
                 device.dptr(hist_hi), int(nbins), _lib.tuning_ptr(self.tuning), stream), "cgb_measure_fused")
         w2, w3, w4 = plan.wide_counts

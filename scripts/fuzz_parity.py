@@ -56,19 +56,25 @@ def check_case(rng, case):
         box[:, 2, 0] = rng.uniform(-1.2, 1.2)
         box[:, 2, 1] = rng.uniform(-1.2, 1.2)
     map_path, bnd_path = sysm.write_files()
-    tune = (int(rng.choice([0, 4096, 8192, 24576])), int(rng.choice([0, 2, 3])), int(rng.choice([0, 16, 128])))
-    lib.cgb_map_set_tuning(*tune)
-    mtune = (int(rng.choice([4096, 12288, 32768])), int(rng.choice([2, 3, 4])))
-    lib.cgb_measure_set_tuning(*mtune)
-    try:
-        cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz_dev))
+    # per-call tuning structs (the library keeps no state)
+    tune = _lib.MapTuning(stage_bytes=int(rng.choice([0, 4096, 8192, 24576])), n_stages=int(rng.choice([0, 2, 3])),
+                          frames_per_cta=int(rng.choice([0, 16, 128])))
+    mtune = _lib.MeasureTuning(stage_bytes=int(rng.choice([0, 4096, 12288, 32768])), n_stages=int(rng.choice([0, 2, 3, 4])),
+                               max_run=int(rng.choice([0, 8, 64])), ctas_per_sm=int(rng.choice([0, 1, 2])))
+    store_values = bool(rng.integers(4))      # a quarter of the cases: statistics-only pass, values measured on demand
+    if True:
+        mapper = Mapping(map_path, options)
+        mapper.tuning = tune
+        cg = mapper.apply(Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz_dev))
         ocg = omap.apply(omap.parse_map(map_path, map_center=options.map_center),
                          oracle_system(sysm.topology, xyz, box))
         got = cg._trajectory.xyz
         assert got.shape == ocg.xyz.shape, "bead array shape"
         assert np.array_equal(got, ocg.xyz), "bead coordinates differ from the oracle"
         bondset = BondSet(bnd_path, options)
-        bondset.apply(cg)
+        bondset.tuning = mtune
+        bondset.staged = bool(rng.integers(8))    # one case in eight through the gather kernels
+        bondset.apply(cg, store_values=store_values)
         bondset.boltzmann_invert()
         terms = obonds.parse_bnd(bnd_path, generate_angles=options.generate_angles,
                                  generate_dihedrals=options.generate_dihedrals)
@@ -165,9 +171,6 @@ def check_case(rng, case):
                 k += 1
                 n_terms += 1
         return kind, n_frames, box_mode, n_terms
-    finally:
-        lib.cgb_map_set_tuning(0, 0, 0)
-        lib.cgb_measure_set_tuning(32768, 3)
 
 
 def main():

@@ -76,6 +76,29 @@ def check_measure_plan(plan):
             assert beads == want
         assert bond == int(plan.col_bond[col])
     assert staged == plan.n_staged
+    # chunk kinds follow the plan's shape; the per-slot lists name every emitting lane-role exactly once
+    shape_kinds = {0: (2, 3, 4, 0), 1: (2, 2, 3, 3)}[int(plan.shape)]
+    lanes = plan.lanes.reshape(-1, 4, 32)
+    for tile in plan.tiles:
+        g0, ng = int(tile["group0"]), int(tile["ngroups"])
+        for g in range(g0, g0 + ng):
+            for c in range(4):
+                k = int(plan.groups[g]["kind"][c])
+                assert k in (0, shape_kinds[c]) and (k != 0 or int(plan.groups[g]["nlanes"][c]) == 0)
+        l0, nslots, nlist = int(tile["list0"]), int(tile["nslots"]), int(tile["nlist"])
+        ptr = plan.tile_lists[l0:l0 + nslots + 1].astype(int)
+        ent = plan.tile_lists[l0 + nslots + 1:l0 + nslots + 1 + nlist].astype(int)
+        assert ptr[0] == 0 and ptr[-1] == nlist and (np.diff(ptr) >= 0).all()
+        seen = set()
+        for slot in range(nslots):
+            for e in ent[ptr[slot]:ptr[slot + 1]]:
+                c, rest = divmod(int(e), 224)
+                gl, lane = divmod(rest, 32)
+                assert gl < ng and int(lanes[g0 + gl, c, lane]["slot"]) == slot
+                seen.add(int(e))
+        want = {c * 224 + (g - g0) * 32 + lane for g in range(g0, g0 + ng) for c in range(4) for lane in range(32)
+                if int(lanes[g, c, lane]["slot"]) >= 0}
+        assert seen == want and len(ent) == len(want)
     # wide columns: after the staged ones, in kind order
     w = sum(plan.wide_counts)
     assert plan.n_staged + w == plan.n_cols

@@ -526,14 +526,14 @@ def test_measure_outputs_stay_inside_their_buffers(options):
     packed.zero_()
     partials, hist = packed[:plan.n_bonds * _lib.NPART], packed[plan.n_bonds * _lib.NPART:]
     box_dev = cg._trajectory.device_box_vectors(dev)
-    for tuning in (None, _lib.MeasureTuning(stage_bytes=8192, n_stages=2, max_run=8, waves=1)):
+    for tuning in (None, _lib.MeasureTuning(stage_bytes=8192, n_stages=2, max_run=8, ctas_per_sm=1)):
         values.fill_(-12345.0)
         packed.zero_()
         _lib.check(_lib.load().cgb_measure_fused(
             device.dptr(cg._trajectory.device_xyz()), device.dptr(box_dev), 1, n_frames, plan.n_beads,
             device.dptr(d["tiles"]), len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]),
-            device.dptr(d["tile_bonds"]), plan.max_span, plan.max_slots, plan.max_edge_chunks, plan.max_tile_groups,
-            device.dptr(st.shift), device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist),
+            device.dptr(d["tile_bonds"]), device.dptr(d["tile_lists"]), plan.shape, plan.max_span, plan.max_slots,
+            plan.max_edge_chunks, plan.max_tile_groups, device.dptr(st.shift), device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist),
             device.dptr(st.hist_lo), device.dptr(st.hist_hi), 128, _lib.tuning_ptr(tuning), device.stream_handle()))
         torch.cuda.synchronize()
         for buf, fill in ((vbuf, -12345.0), (pbuf, -7.0)):

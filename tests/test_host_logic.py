@@ -42,8 +42,8 @@ def test_abi_argument_errors_without_gpu():
     assert lib.cgb_map_tiles(None, None, 0, 10, 2, None, 1, None, None, 8, 8, None, None) == 0   # no frames: no-op
     assert lib.cgb_measure(None, None, 1, -1, 2, None, None, None, 0, 0, 0, 0, None, None, 0, None, None, None, None,
                            0, None) == -1
-    assert lib.cgb_measure_fused(None, None, 1, 5, 2, None, 1, None, None, None, 8, 8, 1, 1, None, None, 0, None, None,
-                                 None, None, 0, None, None) == -1
+    assert lib.cgb_measure_fused(None, None, 1, 5, 2, None, 1, None, None, None, None, 0, 8, 8, 1, 1, None, None, 0,
+                                 None, None, None, None, 0, None, None) == -1
     assert lib.cgb_boltzmann(None, None, None, None, 310.0, 3, None, None, None, 0, 0, None, None) == -1
     assert lib.cgb_allreduce_partials(None, None, 4, None) == -1
     assert lib.cgb_allreduce_partials(None, None, 0, None) == 0       # nothing to reduce: no-op
@@ -226,9 +226,13 @@ def test_measure_plan_covers_every_column(options, system, dihedrals, tmp_path):
     bondset = BondSet(bnd_path, options)
     plan = bondset.compile_plan(cg_top)
     check_measure_plan(plan)
-    assert (plan.tiles["ngroups"] <= _lib.MEAS_WARPS).all() and (plan.tiles["span"] <= 512).all()
+    assert (plan.tiles["ngroups"] <= _lib.MEAS_WARPS).all() and (plan.tiles["span"] <= 384).all()
+    assert plan.shape == (_lib.SHAPE_EAD if plan.counts[2] else _lib.SHAPE_EEAA)
     per_molecule = max(len(bonds) for bonds in bondset._molecules.values())
     assert plan.max_slots <= max(per_molecule, 8)
+    # what the plan asks of a CTA's shared memory fits: tables + histograms + scratch + records + two stages of a quad
+    need = (128 + plan.max_slots * (22 + 4 * 128) + 2 * 897 + 896 * 24 + 7 * 4096 + 2 * (4 * (12 * plan.max_span + 76) + 320))
+    assert need <= 112 * 1024
     if system == "chain":
         assert sum(plan.wide_counts) == 4 and plan.wide_counts == (2, 1, 1)     # the terms that join the two ends
     else:

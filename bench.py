@@ -253,20 +253,10 @@ def measure_leg(dev, peak_gbs, workload="s3"):
     st = bonds._state
     plan = st.plan
     n2, n3, n4 = plan.counts
-    d = BondSet._device_plan(plan, dev)
-    cgx = cg._trajectory.device_xyz()
-    box_dev = cg._trajectory.device_box_vectors(dev)
-    lo, hi = torch.from_numpy(st.hist_lo).to(dev), torch.from_numpy(st.hist_hi).to(dev)
-    stream = device.stream_handle()
 
     def kernels():
-        st.partials.zero_()
-        st.hist.zero_()
-        _lib.check(lib.cgb_measure(device.dptr(cgx), device.dptr(box_dev), 1, n_frames, plan.n_beads,
-                                   device.dptr(d["col_beads"]), device.dptr(d["col_bond"]), device.dptr(d["col_slot"]),
-                                   plan.max_slots, device.dptr(d["tile_span"]), plan.max_span, n2, n3, n4, plan.n_bonds,
-                                   device.dptr(st.shift), device.dptr(st.values), device.dptr(st.partials),
-                                   device.dptr(st.hist), device.dptr(lo), device.dptr(hi), 128, stream))
+        st.packed.zero_()
+        bonds._launch_measure(plan, st.source, n_frames, st.shift, st.values, st.packed, 128, st.hist_lo, st.hist_hi)
 
     for _ in range(2):
         kernels()
@@ -292,9 +282,9 @@ def measure_leg(dev, peak_gbs, workload="s3"):
         label += f": {plan.n_beads:,} beads, {n_terms:,} terms per frame ({n2:,} bonds, {n3:,} angles, {n4:,} dihedrals)"
     return {"workload": label,
             "value": measures / (ms * 1e-3), "unit": "bond-measures/s", "ms_per_pass": ms,
-            "includes": "values + moments + circular sums + 128-bin histograms (one measure_tiles_kernel launch per kind)",
+            "includes": "values + moments + circular sums + 128-bin histograms, ONE measure_fused_kernel launch for all kinds",
             "api_ms_per_pass": api_ms, "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs,
-            "frac_of_hbm_peak": gbs / peak_gbs, "bound": "instruction issue (acos/atan2 per measure), not HBM",
+            "frac_of_hbm_peak": gbs / peak_gbs, "bound": "instruction issue (atan2 / histogram per measure), not HBM",
             "boltzmann_invert_ms": invert_ms}
 
 

@@ -1,8 +1,10 @@
 """World-size-2 test of the frame-sharded path over gloo (CPU).
 
 The GPU kernels are not run here; what is covered is the host logic of the
-multi-GPU path: contiguous frame shards, one all-reduce(sum) over the packed
-per-bond partial moments + histogram, and that the merged partials invert to the
+multi-GPU path: contiguous frame shards, ONE all-reduce(sum) over the packed float64
+buffer [per-bond partial moments | histogram counts] (``dist.allreduce_packed``: gloo
+for host tensors, the library's ``cgb_allreduce_partials`` for device tensors), the
+one-pass circular variance of dihedrals, and that the merged partials invert to the
 same parameters as a single pass.  The per-shard partials are produced by a
 float64 NumPy statement of the accumulator definitions in
 ``include/pycgtool_b200.h`` (test scaffolding), the expected parameters by the oracle.
@@ -25,6 +27,8 @@ def _partials_of(values, natoms, shift):
     """One CGB_NPART row from a value array, by definition (header, stage 2)."""
     v = values[np.isfinite(values)].astype(np.float64)
     d = v - shift
+    if natoms == 4:
+        d -= 2 * np.pi * np.rint(d / (2 * np.pi))       # dihedrals: wrapped about the shift
     return np.array([len(v), d.sum(), (d * d).sum(), np.cos(v).sum(), np.sin(v).sum(), 0.0, len(values), 0.0])
 
 
@@ -40,7 +44,10 @@ def _invert_row(row, natoms, shift, form, temp=310.0):
             e = mean - shift
             var = (row[2] - 2 * e * row[1]) / n + e * e
         else:
-            var = row[5] / n
+            # one pass: exact when no sample lies between the antipodes of shift and mean (cgb_boltzmann)
+            e = mean - shift
+            e -= 2 * math.pi * round(e / (2 * math.pi))
+            var = (row[2] - 2 * e * row[1]) / n + e * e
     eqm = ((mean) % (2 * math.pi)) - math.pi if natoms == 4 else mean
     return eqm, ostats.force_constant(form, mean, var, temp)
 
@@ -65,18 +72,13 @@ def _worker(rank, world, port, tmpdir):
         dist.broadcast(shift, src=0)
         assert shift[0].item() == float(data[2][0, 0])
         rows = [_partials_of(data[k][begin:end].reshape(-1), k, float(shift[i])) for i, k in enumerate((2, 3, 4))]
-        partials = torch.from_numpy(np.stack(rows))
-        hist = torch.from_numpy(np.stack([np.histogram(data[k][begin:end], bins=16, range=r)[0] for k, r in
-                                          ((2, (0, 2)), (3, (0, np.pi)), (4, (-np.pi, np.pi)))]).astype(np.int64))
-        dist.allreduce_sum(partials)
-        dist.allreduce_sum(hist)
-        # pass 2 for the dihedral row uses the reduced circular mean, then a second small all-reduce
-        mean4 = math.atan2(partials[2, 4].item(), partials[2, 3].item())
-        d = data[4][begin:end].reshape(-1).astype(np.float64) - mean4
-        d -= 2 * np.pi * np.rint(d / (2 * np.pi))
-        wrapped = torch.tensor([float((d * d).sum())], dtype=torch.float64)
-        dist.allreduce_sum(wrapped)
-        partials[2, 5] = wrapped[0]
+        hist = np.stack([np.histogram(data[k][begin:end], bins=16, range=r)[0] for k, r in
+                         ((2, (0, 2)), (3, (0, np.pi)), (4, (-np.pi, np.pi)))]).astype(np.float64)
+        # ONE packed float64 buffer [partials | hist] crosses the ranks, as in _MeasureState.invert
+        packed = torch.from_numpy(np.concatenate([np.stack(rows).reshape(-1), hist.reshape(-1)]))
+        dist.allreduce_packed(packed)
+        partials = packed[:3 * 8].view(3, 8)
+        hist = packed[3 * 8:].view(3, 16)
         assert dist.all_true(True) and not dist.all_true(rank == 0)
         for i, (k, form) in enumerate(((2, "Harmonic"), (3, "CosHarmonic"), (4, "Harmonic"))):
             eqm, fc = _invert_row(partials[i].numpy(), k, float(shift[i]), form)

@@ -92,6 +92,16 @@ int cgb_map_plan_build(const int32_t* bead_ptr, const int32_t* index, const void
                        int32_t max_span_atoms, int32_t max_tile_beads,
                        CgbMapTile* tiles, CgbMapEntry* entries, double* entries_w64);
 
+/* The same two passes with forced cuts: tile_start (HOST uint8 [n_beads], or NULL) is 1 where a tile must begin.
+ * Used by the fused mapping + measurement path, whose mapping tiles follow the measurement plan's units. */
+int cgb_map_plan_size_cuts(const int32_t* bead_ptr, const int32_t* index, const uint8_t* compute, int64_t n_beads,
+                           int64_t n_atoms, int32_t max_span_atoms, int32_t max_tile_beads, const uint8_t* tile_start,
+                           int64_t* n_tiles, int64_t* n_entries, int32_t* max_span, int32_t* max_tile_entries);
+int cgb_map_plan_build_cuts(const int32_t* bead_ptr, const int32_t* index, const void* weights, int weights_f64,
+                            const uint8_t* compute, int64_t n_beads, int64_t n_atoms, int32_t max_span_atoms,
+                            int32_t max_tile_beads, const uint8_t* tile_start, CgbMapTile* tiles, CgbMapEntry* entries,
+                            double* entries_w64);
+
 /* K1: tiled mapping kernel.  xyz: device float32 [F][N][3]; box_len: device float32 [F][3] or NULL
  * (no periodic unwrap -- the caller passes NULL when the frame has no box or any length of any frame
  * is zero, mapping.py:406-408); tiles/entries(/entries_w64): device copies of the plan; cg_xyz: device
@@ -220,14 +230,19 @@ int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t want_slots, i
  * Pass 1 sizes the arrays; pass 2 fills them: tiles[n_tiles], groups[n_groups],
  * lanes[n_groups][CGB_MEAS_CHUNKS][32], tile_bonds[n_tile_bonds], tile_lists[n_tile_lists] (uint16),
  * col_out[M] (position of every column in the values row; wide columns follow the staged ones, in kind
- * order) and wide_cols[n_wide] (the columns left to cgb_measure). */
+ * order) and wide_cols[n_wide] (the columns left to cgb_measure).
+ * unit_groups = 0: tiles are packed freely (cgb_measure_fused).  unit_groups > 0: the plan of the fused mapping +
+ * measurement kernel (cgb_map_measure): every tile is a run of whole units -- bead ranges no term straddles, e.g.
+ * one molecule instance -- of at most max_span beads and unit_groups groups, so tiles are disjoint bead ranges;
+ * tile_start (uint8 [n_beads], may be NULL) receives 1 where such a tile begins and right after it ends: the cuts the
+ * mapping plan must respect (cgb_map_plan_size/build, tile_start).  CGB_ETOOBIG when a unit does not fit. */
 int cgb_measure_plan_size(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
-                          int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape,
+                          int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape, int32_t unit_groups,
                           CgbMeasPlanInfo* info);
 int cgb_measure_plan_build(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3, int64_t n4,
-                           int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape, CgbMeasTile* tiles,
-                           CgbMeasGroup* groups, CgbMeasLane* lanes, int32_t* tile_bonds, uint16_t* tile_lists,
-                           int32_t* col_out, int64_t* wide_cols);
+                           int64_t n_beads, int32_t max_span, int32_t max_slots, int32_t shape, int32_t unit_groups,
+                           CgbMeasTile* tiles, CgbMeasGroup* groups, CgbMeasLane* lanes, int32_t* tile_bonds,
+                           uint16_t* tile_lists, int32_t* col_out, int64_t* wide_cols, uint8_t* tile_start);
 
 /* Benchmarking knobs of K2, passed per call (NULL or a zero field keeps the default). */
 typedef struct CgbMeasureTuning {
@@ -254,6 +269,22 @@ int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int ortho, int6
 int cgb_measure_fused_config(int64_t n_frames, int64_t n_beads, int64_t n_tiles, int32_t max_span, int32_t max_slots,
                              int32_t max_edge_chunks, int32_t max_tile_groups, int32_t n_bins, int with_hist,
                              const CgbMeasureTuning* tuning, int32_t sm_count, int64_t* out);
+
+/* ---- stages 1 + 2 fused: mapping warps hand every mapped tile, still in shared memory, to measurement warps, so
+ * the CG trajectory is written once and never read back (reference call sequence: pycgtool/__main__.py:69-112).
+ * Mapping plan: cgb_map_plan_build_cuts with the tile_start of a measurement plan compiled with unit_groups = 2,
+ * max_span = max_tile_beads; meas_of_tile: device int32 [n_tiles], the measurement tile that covers exactly the bead
+ * range of mapping tile i, or -1 (solvent).  float32 weights only; every measured bead must be computed by a tile.
+ * box_len: device float32 [F][3] or NULL (mapping, mapping.py:406-408); box_vec / ortho as in cgb_measure_fused.
+ * cg_xyz is written for all tiles; values / partials / hist as in cgb_measure_fused. */
+int cgb_map_measure(const float* xyz, const float* box_len, const float* box_vec, int ortho, int64_t n_frames,
+                    int64_t n_atoms, int64_t n_beads, const CgbMapTile* tiles, int64_t n_tiles,
+                    const CgbMapEntry* entries, int32_t max_span, int32_t max_tile_entries, int32_t max_tile_beads,
+                    float* cg_xyz, const int32_t* meas_of_tile, const CgbMeasTile* meas_tiles,
+                    const CgbMeasGroup* groups, const CgbMeasLane* lanes, const int32_t* tile_bonds,
+                    const uint16_t* tile_lists, int32_t shape, int32_t max_slots, const float* shift, float* values,
+                    int64_t row_stride, double* partials, double* hist, const float* hist_lo, const float* hist_hi,
+                    int32_t n_bins, void* stream);
 
 /* ---- gather kernels: columns straight from global memory (wide columns, or callers without a plan) ----
  * col_slot: device int32 [M] or NULL.  Inside every group of CGB_MEASURE_TILE consecutive columns of one

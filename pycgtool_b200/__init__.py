@@ -12,7 +12,8 @@ from .frame import Frame
 from .mapping import BeadMap, Mapping, VirtualMap
 from .bondset import Bond, BondSet
 from .functionalforms import FunctionalForm, get_functional_forms
+from .pipeline import map_and_measure
 
 __version__ = "0.1.0"
 __all__ = ["Frame", "Mapping", "BeadMap", "VirtualMap", "BondSet", "Bond", "FunctionalForm",
-           "get_functional_forms"]
+           "get_functional_forms", "map_and_measure"]

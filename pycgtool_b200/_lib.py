@@ -102,17 +102,21 @@ SIGNATURES = {
     "cgb_abi_version": (_int, []),
     "cgb_map_plan_size": (_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cgb_map_plan_build": (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "cgb_map_plan_size_cuts": (_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cgb_map_plan_build_cuts": (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cgb_map_tiles": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "cgb_map_tiles_window": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "cgb_copy_window_h2d": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cgb_map_gather": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _vp]),
     "cgb_map_tiles_ex": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "cgb_measure_plan_limits": (_int, [_i32, _int, _i32, _vp, _vp]),
-    "cgb_measure_plan_size": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp]),
-    "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
-                                      _vp, _vp]),
+    "cgb_measure_plan_size": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp]),
     "cgb_measure_fused": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                  _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "cgb_map_measure": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cgb_measure_fused_config": (_int, [_i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _int, _vp, _i32, _vp]),
     "cgb_measure": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i64, _i64,
                            _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),

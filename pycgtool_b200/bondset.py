@@ -462,7 +462,7 @@ class BondSet:
         return out
 
     # ------------------------------------------------------------------ plan (bondset.py:507-528)
-    def compile_plan(self, topology):
+    def compile_plan(self, topology, fused=None):
         """Resolve every bond's bead names to bead indices for all instances.
 
         One instance per residue whose name equals the molecule; a name prefixed
@@ -538,15 +538,18 @@ class BondSet:
             if len(cols):
                 plan.bond_first[b] = plan.col_beads[cols[0]]
                 plan.natoms_measured[b] = plan.natoms[b]
-        self._compile_kernel_plan(plan)
+        if not self._compile_kernel_plan(plan, fused):
+            return None           # fused=(groups, beads): a unit of the system does not fit a fused tile
         # from column numbers to positions in the values row
         plan.bond_columns = plan.bond_cols
         plan.bond_cols = [plan.col_out[cols].astype(np.int64) for cols in plan.bond_columns]
         return plan
 
-    def _compile_kernel_plan(self, plan):
+    def _compile_kernel_plan(self, plan, fused=None):
         """Tiles / groups / lanes of the fused kernel (``cgb_measure_plan_*``, host code in the library) and the
-        sub-table of the columns left to the gather kernels."""
+        sub-table of the columns left to the gather kernels.  ``fused=(groups, beads)``: the unit-aligned plan of
+        ``cgb_map_measure`` (tiles of whole molecule instances, at most ``beads`` beads and ``groups`` groups);
+        returns False when the system cannot be tiled that way."""
         import ctypes
         lib = _lib.load()
         n2, n3, n4 = plan.counts
@@ -566,12 +569,19 @@ class BondSet:
         plan.tile_bonds = np.zeros(0, dtype=np.int32)
         plan.tile_lists = np.zeros(0, dtype=np.uint16)
         plan.shape = _lib.SHAPE_EAD if n4 else _lib.SHAPE_EEAA
-        if self.staged and n_cols:
+        plan.tile_start = None
+        if (self.staged or fused) and n_cols:
             info = _lib.MeasPlanInfo()
             slots = max_slots.value
+            unit_groups, span = (0, max_span.value) if fused is None else (int(fused[0]), min(int(fused[1]), max_span.value))
             args = (_lib.ptr(plan.col_beads), _lib.ptr(plan.col_bond), n2, n3, n4, plan.n_beads,
-                    max_span.value, slots, plan.shape)
-            _lib.check(lib.cgb_measure_plan_size(*args, ctypes.byref(info)), "cgb_measure_plan_size")
+                    span, slots, plan.shape, unit_groups)
+            rc = lib.cgb_measure_plan_size(*args, ctypes.byref(info))
+            if fused is not None and rc == -3:
+                return False
+            _lib.check(rc, "cgb_measure_plan_size")
+            if fused is not None:
+                plan.tile_start = np.zeros(plan.n_beads, dtype=np.uint8)
             plan.tiles = np.zeros(info.n_tiles, dtype=_lib.MEAS_TILE_DTYPE)
             plan.groups = np.zeros(info.n_groups, dtype=_lib.MEAS_GROUP_DTYPE)
             plan.lanes = np.zeros(info.n_groups * _lib.MEAS_CHUNKS * 32, dtype=_lib.MEAS_LANE_DTYPE)
@@ -580,8 +590,8 @@ class BondSet:
             wide = np.zeros(info.n_wide, dtype=np.int64)
             _lib.check(lib.cgb_measure_plan_build(*args, _lib.ptr(plan.tiles), _lib.ptr(plan.groups),
                                                   _lib.ptr(plan.lanes), _lib.ptr(plan.tile_bonds),
-                                                  _lib.ptr(plan.tile_lists), _lib.ptr(plan.col_out), _lib.ptr(wide)),
-                       "cgb_measure_plan_build")
+                                                  _lib.ptr(plan.tile_lists), _lib.ptr(plan.col_out), _lib.ptr(wide),
+                                                  _lib.ptr(plan.tile_start)), "cgb_measure_plan_build")
             plan.n_staged = int(info.n_staged)
             plan.max_span, plan.max_slots = int(info.max_span), int(info.max_slots)
             plan.max_edge_chunks, plan.max_tile_groups = int(info.max_edge_chunks), int(info.max_tile_groups)
@@ -591,6 +601,7 @@ class BondSet:
         plan.wide_beads = np.ascontiguousarray(plan.col_beads[wide])
         plan.wide_bond = np.ascontiguousarray(plan.col_bond[wide])
         plan.wide_slot, plan.wide_max_slots = self._tile_slots(plan.wide_bond, w_counts)
+        return True
 
     @staticmethod
     def _tile_slots(col_bond, counts):

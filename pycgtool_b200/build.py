@@ -13,8 +13,10 @@ import shutil
 import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
-SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_measure_fused.cu", "cgb_boltzmann.cu", "cgb_xtc.cu", "cgb_comm.cu"]
-HEADERS = [CSRC / "cgb_common.cuh", CSRC / "cgb_terms.cuh", CSRC / "cgb_measure_plan.cpp.inc",
+SOURCES = ["cgb_map.cu", "cgb_measure.cu", "cgb_measure_fused.cu", "cgb_map_measure.cu", "cgb_boltzmann.cu",
+           "cgb_xtc.cu", "cgb_comm.cu"]
+HEADERS = [CSRC / "cgb_common.cuh", CSRC / "cgb_terms.cuh", CSRC / "cgb_termwarp.cuh", CSRC / "cgb_mapwarp.cuh",
+           CSRC / "cgb_measure_plan.cpp.inc",
            CSRC.parent.parent / "include" / "pycgtool_b200.h"]
 LIBRARY = CSRC / "libpycgtool_b200.so"
 STAMP = CSRC / ".build_stamp"

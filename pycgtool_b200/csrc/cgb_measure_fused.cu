@@ -22,15 +22,13 @@
 #include <algorithm>
 #include <cstring>
 
-#include "cgb_terms.cuh"
+#include "cgb_termwarp.cuh"
 #include "cgb_measure_plan.cpp.inc"
 
 namespace cgb {
 
-constexpr int kWarps = CGB_MEAS_WARPS;            // consumer warps per CTA
-constexpr int kConsumers = kWarps * 32;
-constexpr int kChunks = CGB_MEAS_CHUNKS;
-constexpr int kRoles = kChunks * kConsumers;      // lane-roles of a CTA (chunk, warp, lane)
+constexpr int kWarps = kTermWarps;                // consumer warps per CTA
+constexpr int kConsumers = kTermThreads;
 constexpr int kStagesMax = 4;
 
 struct FusedParams {
@@ -63,29 +61,6 @@ struct FusedParams {
     int32_t ecache_warp_bytes;
     // shared-memory map (byte offsets)
     int32_t off_sparam, off_shist, off_lists, off_eacc, off_nbad, off_ecache, off_stages;
-};
-
-// Kind of chunk c in a group of the given shape (0: unused).
-template <int SHAPE>
-__host__ __device__ constexpr int chunk_kind(int c) {
-    return SHAPE == CGB_SHAPE_EAD ? (c == 0 ? 2 : (c == 1 ? 3 : (c == 2 ? 4 : 0))) : (c < 2 ? 2 : 3);
-}
-
-// Edge records of a warp: [frame pair][half of the record][edge][16 bytes].  Strides by shape (compile time).
-template <int SHAPE>
-struct RecLayout {
-    static constexpr int kEdges = SHAPE == CGB_SHAPE_EAD ? 32 : 64;
-    static constexpr int kHalf = kEdges * 16;       // bytes between the two halves of a record
-    static constexpr int kPair = 2 * kHalf;         // bytes between the records of the two frame pairs
-    static constexpr int kWarpBytes = 2 * kPair;
-};
-
-// Per-lane state of one chunk of the warp's group.
-struct Role {
-    uint32_t a0, a1, a2;   // edge: byte offsets of the two beads in a staged frame; angle / dihedral: record offsets
-    float g1, g2;          // orientation signs
-    f2 s1, s2, c, s;       // float32 sums of this CTA segment: d, d^2, cos, sin (two frames per register pair)
-    int slot;              // tile-local Bond slot, -1: the lane produces no column
 };
 
 // The share of the work items (tile-major, frame-block-minor) of one CTA, cut into segments: consecutive blocks of
@@ -247,10 +222,26 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     // ---------------------------------------------------------------------- consumer warps
     using Rec = RecLayout<SHAPE>;
     const uint32_t ecache32 = smem_u32(smem + q.off_ecache) + (uint32_t)warp * (uint32_t)Rec::kWarpBytes;
-    const uint32_t shist32 = smem_u32(shist);
+    TermTables tabs;
+    tabs.sbond = sbond;
+    tabs.sparam = sparam;
+    tabs.shist = shist;
+    tabs.slist = slist;
+    tabs.snbad = snbad;
+    tabs.eacc = eacc;
+    tabs.ecnt = ecnt;
+    tabs.shist32 = smem_u32(shist);
+    tabs.shift = q.shift;
+    tabs.hlo = q.hlo;
+    tabs.hhi = q.hhi;
+    tabs.values = q.values;
+    tabs.row_stride = q.row_stride;
+    tabs.partials = q.partials;
+    tabs.hist = q.hist;
+    tabs.nbins = q.nbins;
     const bool store = q.values != nullptr;  // uniform
-    const int nbins = q.nbins;
     const int64_t row_stride = q.row_stride;
+    TermWarp<MIC, SHAPE> tw;
     int s = 0;
     uint32_t phase = 0;
 
@@ -263,273 +254,11 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
         const bool working = warp < ng * fl;
         const int gi = working ? warp % ng : 0;
         const int fli = warp / ng;                   // this warp's frame lane
-        const CgbMeasGroup grp = q.groups[tile.group0 + gi];
         const uint32_t h0 = (uint32_t)(reinterpret_cast<uintptr_t>(q.xyz + (size_t)tile.bead0 * 3) & 15u);
-        for (int i = tid; i < tile.nslots; i += kConsumers) {
-            const int bond = __ldg(q.tile_bonds + tile.slot0 + i);
-            sbond[i] = bond;
-            float4 prm = make_float4(q.shift ? -__ldg(q.shift + bond) : 0.f, 0.f, 0.f, 0.f);
-            if (do_hist) {
-                const float lo = __ldg(q.hlo + bond), hi = __ldg(q.hhi + bond);
-                prm.y = (float)nbins / (hi - lo);
-                prm.z = fmaf(-lo, prm.y, -0.5f);
-            }
-            sparam[i] = prm;
-        }
-        if (do_hist)
-            for (int i = tid; i < tile.nslots * nbins; i += kConsumers) shist[i] = 0u;
-        for (int i = tid; i < tile.nslots + 1 + tile.nlist; i += kConsumers) slist[i] = __ldg(q.tile_lists + tile.list0 + i);
-        for (int i = tid; i < kRoles; i += kConsumers) snbad[i] = 0u;
-
-        Role role[kChunks];
-        int nl[kChunks], ne[kChunks];                // active / emitting lanes of each chunk (uniform)
-        int vcol[kChunks];                           // this lane's position in the values row, per chunk
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            Role& r = role[c];
-            r.a0 = r.a1 = r.a2 = 0;
-            r.g1 = r.g2 = 1.f;
-            r.s1 = r.s2 = r.c = r.s = 0;
-            r.slot = -1;
-            constexpr int kNone = 0;
-            const int kind = chunk_kind<SHAPE>(c);
-            nl[c] = (working && kind != kNone) ? grp.nlanes[c] : 0;
-            ne[c] = (working && kind != kNone) ? grp.nemit[c] : 0;
-            vcol[c] = grp.vcol0[c] + lane;
-            if (lane >= nl[c]) continue;
-            const CgbMeasLane ln = q.lanes[((size_t)(tile.group0 + gi) * kChunks + c) * 32 + lane];
-            if (kind == 2) {
-                r.a0 = (ln.ref & 0xffffu) * 12u + h0;
-                r.a1 = (ln.ref >> 16) * 12u + h0;
-                r.a2 = ecache32 + (uint32_t)(c * 32 + lane) * 16u;      // where this lane leaves its records
-            } else {
-                const uint32_t e0 = ln.ref & 0x7fu, e1 = (ln.ref >> 8) & 0x7fu, e2 = (ln.ref >> 16) & 0x7fu;
-                const float s0 = (ln.ref & 0x80u) ? -1.f : 1.f, s1 = (ln.ref & 0x8000u) ? -1.f : 1.f,
-                            s2 = (ln.ref & 0x800000u) ? -1.f : 1.f;
-                r.a0 = ecache32 + e0 * 16u;                            // shared-memory addresses of the records
-                r.a1 = ecache32 + e1 * 16u;
-                r.a2 = ecache32 + e2 * 16u;
-                if (kind == 3) {
-                    r.g1 = s0 * s1;
-                } else {
-                    r.g1 = s0 * s1 * s2;
-                    r.g2 = s0 * s2;
-                }
-            }
-            r.slot = ln.slot;
-        }
-        int frames_done = 0;                     // frames this warp has evaluated in this segment (uniform)
+        term_tables_fill(tabs, tile, q.tile_bonds, q.tile_lists, tid, kConsumers);
+        tw.setup(working, q.groups[tile.group0 + gi], q.lanes + (size_t)(tile.group0 + gi) * kChunks * 32, lane, h0,
+                 ecache32, tid);
         asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
-
-        // Exact-rule histogram update of one value (next to a bin edge, out of range or NaN: ~0.02 % of the values).
-        auto hist_exact = [&](int slot, float v) {
-            const int bond = sbond[slot];
-            hist_add_exact(shist + slot * nbins, v, __ldg(q.hlo + bond), __ldg(q.hhi + bond), nbins);
-        };
-        // Statistics, histogram and stores of the two evaluated frame pairs of a quad (the common case: all four
-        // frames valid).  Straight-line code up to the one rare branch at its end, so that the two pairs' dependency
-        // chains -- and the evaluation before them -- interleave.
-        auto finish_fast = [&](Role& r, int kind, f2 va, f2 cva, f2 sva, f2 vb, f2 cvb, f2 svb, float* out) {
-            const float4 prm = sparam[r.slot];
-            const f2 nshift2 = splat2(prm.x);
-            const f2 da = kind == 4 ? wrap_about2(va, nshift2) : add2(va, nshift2);
-            const f2 db = kind == 4 ? wrap_about2(vb, nshift2) : add2(vb, nshift2);
-            r.s1 = add2(r.s1, add2(da, db));
-            r.s2 = fma2(db, db, fma2(da, da, r.s2));
-            if (kind != 2) {
-                r.c = add2(r.c, add2(cva, cvb));
-                r.s = add2(r.s, add2(sva, svb));
-            }
-            if (store) {
-                __stcs(out, lo2(va));
-                __stcs(out + row_stride, hi2(va));
-                __stcs(out + 2 * row_stride, lo2(vb));
-                __stcs(out + 3 * row_stride, hi2(vb));
-            }
-            if (do_hist) {
-                const f2 hn = splat2(prm.y), hc = splat2(prm.z);
-                const uint32_t row_adj = shist32 + (uint32_t)(r.slot * nbins) * 4u - 4u * 0x4b000000u;
-                const unsigned redo = hist_add_pair_pred(row_adj, va, hn, hc, (unsigned)nbins) |
-                                      (hist_add_pair_pred(row_adj, vb, hn, hc, (unsigned)nbins) << 2);
-                if (redo) {
-                    if (redo & 1u) hist_exact(r.slot, lo2(va));
-                    if (redo & 2u) hist_exact(r.slot, hi2(va));
-                    if (redo & 4u) hist_exact(r.slot, lo2(vb));
-                    if (redo & 8u) hist_exact(r.slot, hi2(vb));
-                }
-            }
-        };
-        // One value on its own (rare): a frame next to the end of the trajectory or a degenerate / NaN operand.
-        auto finish_one = [&](Role& r, int kind, int c, int half, float v, float cv, float sv, float* out) {
-            if (store) __stcs(out, v);
-            if (!(v == v)) {  // NaN-skipping statistics (np.nanmean / np.nanvar, util.py:36,53)
-                snbad[c * kConsumers + tid] += 1u;
-                return;
-            }
-            const float4 prm = sparam[r.slot];
-            const f2 vv = half ? pack2(0.f, v) : pack2(v, 0.f);
-            const f2 ns = half ? pack2(0.f, prm.x) : pack2(prm.x, 0.f);
-            const f2 d = kind == 4 ? wrap_about2(vv, ns) : add2(vv, ns);
-            r.s1 = add2(r.s1, d);
-            r.s2 = fma2(d, d, r.s2);
-            if (kind != 2) {
-                r.c = add2(r.c, half ? pack2(0.f, cv) : pack2(cv, 0.f));
-                r.s = add2(r.s, half ? pack2(0.f, sv) : pack2(sv, 0.f));
-            }
-            if (do_hist) {
-                const int bond = sbond[r.slot];
-                const int bin = hist_bin(v, __ldg(q.hlo + bond), __ldg(q.hhi + bond), prm.y, nbins);
-                if (bin >= 0) atomicAdd(shist + r.slot * nbins + bin, 1u);
-            }
-        };
-        auto pick = [](int i, f2 a, f2 b) {  // frame i (0..3) of the two pairs of a quad
-            const f2 x = i < 2 ? a : b;
-            return (i & 1) ? hi2(x) : lo2(x);
-        };
-
-        // One quad (frames 4 qd .. 4 qd + 3 of the stage, `nvalid` of them inside the trajectory) of this warp's group.
-        auto do_quad = [&](const unsigned char* fq, const float* tq, float* vq, int nvalid) {
-            const bool whole = nvalid == 4;
-            // ---- edges: displacement records of both frame pairs, and the lengths
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                if (chunk_kind<SHAPE>(c) != 2) continue;
-                Role& r = role[c];
-                if (lane < nl[c]) {
-                    EdgeRec e[2];
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const unsigned char* fa = fq + (size_t)(2 * pp) * q.slot_bytes;
-                        const unsigned char* fb = fa + q.slot_bytes;
-                        if (MIC == MIC_TRICLINIC) {
-                            float rr[2][3];
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                Box bx;
-                                const float4* t = reinterpret_cast<const float4*>(tq + (2 * pp + h) * 12);
-                                const float4 t0 = t[0], t1 = t[1], t2 = t[2];
-                                bx.a[0] = t0.x; bx.a[1] = t0.y; bx.a[2] = t0.z;
-                                bx.b[0] = t1.x; bx.b[1] = t1.y; bx.b[2] = t1.z;
-                                bx.c[0] = t2.x; bx.c[1] = t2.y; bx.c[2] = t2.z;
-                                const unsigned char* fr = h ? fb : fa;
-                                const float* xa = reinterpret_cast<const float*>(fr + r.a0);
-                                const float* xb = reinterpret_cast<const float*>(fr + r.a1);
-                                const float pa[3] = {xa[0], xa[1], xa[2]}, pb[3] = {xb[0], xb[1], xb[2]};
-                                edge_triclinic(pa, pb, bx, rr[h]);
-                            }
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) e[pp].r[d] = pack2(rr[0][d], rr[1][d]);
-                            edge_norm2(e[pp]);
-                        } else {
-                            const float* xa0 = reinterpret_cast<const float*>(fa + r.a0);
-                            const float* xa1 = reinterpret_cast<const float*>(fb + r.a0);
-                            const float* xb0 = reinterpret_cast<const float*>(fa + r.a1);
-                            const float* xb1 = reinterpret_cast<const float*>(fb + r.a1);
-                            f2 xa[3], xb[3];
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                xa[d] = pack2(xa0[d], xa1[d]);
-                                xb[d] = pack2(xb0[d], xb1[d]);
-                            }
-                            const ulonglong2* t = reinterpret_cast<const ulonglong2*>(tq + pp * 12);
-                            const ulonglong2 q0 = t[0], q1 = t[1], q2 = t[2];
-                            const f2 nL[3] = {q0.x, q0.y, q1.x}, inv[3] = {q1.y, q2.x, q2.y};
-                            edge_pair<MIC_ORTHO>(xa, xb, nL, inv, e[pp]);
-                        }
-                    }
-                    // the records in two 16-byte halves, each in its own array: conflict-free 128-bit accesses
-                    sts_v2u64<0>(r.a2, e[0].r[0], e[0].r[1]);
-                    sts_v2u64<Rec::kHalf>(r.a2, e[0].r[2], e[0].n2);
-                    sts_v2u64<Rec::kPair>(r.a2, e[1].r[0], e[1].r[1]);
-                    sts_v2u64<Rec::kPair + Rec::kHalf>(r.a2, e[1].r[2], e[1].n2);
-                    if (lane < ne[c]) {
-                        float* out = vq + vcol[c];
-                        f2 va, vb;
-                        const bool oka = length_pair(e[0].n2, va), okb = length_pair(e[1].n2, vb);
-                        if (oka && okb && whole) {
-                            finish_fast(r, 2, va, 0, 0, vb, 0, 0, out);
-                        } else {
-#pragma unroll 1
-                            for (int i = 0; i < nvalid; ++i) {
-                                const bool ok = i < 2 ? oka : okb;
-                                const float v = ok ? pick(i, va, vb) : __fsqrt_rn(pick(i, e[0].n2, e[1].n2));
-                                finish_one(r, 2, c, i & 1, v, 0.f, 0.f, out + (size_t)i * row_stride);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-
-            // ---- angles and dihedrals from the records
-            auto load_rec = [&](int pp, uint32_t addr, EdgeRec& e) {
-                if (pp == 0) {
-                    lds_v2u64<0>(addr, e.r[0], e.r[1]);
-                    lds_v2u64<Rec::kHalf>(addr, e.r[2], e.n2);
-                } else {
-                    lds_v2u64<Rec::kPair>(addr, e.r[0], e.r[1]);
-                    lds_v2u64<Rec::kPair + Rec::kHalf>(addr, e.r[2], e.n2);
-                }
-            };
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                constexpr int kNone = 0;
-                const int kind = chunk_kind<SHAPE>(c);
-                if (kind == kNone || kind == 2) continue;
-                Role& r = role[c];
-                if (lane < nl[c]) {
-                    float* out = vq + vcol[c];
-                    if (kind == 3) {
-                        f2 v2[2], cv2[2], sv2[2], den[2];
-                        bool ok[2];
-#pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) {
-                            EdgeRec u, v;
-                            load_rec(pp, r.a0, u);
-                            load_rec(pp, r.a1, v);
-                            ok[pp] = angle_pair(u, v, r.g1, v2[pp], cv2[pp], sv2[pp], den[pp]);
-                        }
-                        if (ok[0] && ok[1] && whole) {
-                            finish_fast(r, 3, v2[0], cv2[0], sv2[0], v2[1], cv2[1], sv2[1], out);
-                        } else {
-#pragma unroll 1
-                            for (int i = 0; i < nvalid; ++i) {
-                                const float dn = pick(i, den[0], den[1]);
-                                const bool good = dn > 0.f && dn < 3e38f;
-                                const float val = good ? pick(i, v2[0], v2[1]) : __int_as_float(0x7fc00000);
-                                finish_one(r, 3, c, i & 1, val, pick(i, cv2[0], cv2[1]), pick(i, sv2[0], sv2[1]),
-                                           out + (size_t)i * row_stride);
-                            }
-                        }
-                    } else {
-                        f2 v2[2], cv2[2], sv2[2], p1[2], p2[2];
-                        bool ok[2];
-#pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) {
-                            EdgeRec b1, b2, b3;
-                            load_rec(pp, r.a0, b1);
-                            load_rec(pp, r.a1, b2);
-                            load_rec(pp, r.a2, b3);
-                            ok[pp] = dihedral_pair(b1, b2, b3, r.g1, r.g2, v2[pp], cv2[pp], sv2[pp], p1[pp], p2[pp]);
-                        }
-                        if (ok[0] && ok[1] && whole) {
-                            finish_fast(r, 4, v2[0], cv2[0], sv2[0], v2[1], cv2[1], sv2[1], out);
-                        } else {
-#pragma unroll 1
-                            for (int i = 0; i < nvalid; ++i) {
-                                const float x1 = pick(i, p1[0], p1[1]), x2 = pick(i, p2[0], p2[1]);
-                                const float rr = fmaf(x1, x1, x2 * x2);
-                                float cv = pick(i, cv2[0], cv2[1]), sv = pick(i, sv2[0], sv2[1]);
-                                float val = pick(i, v2[0], v2[1]);
-                                if (!(rr > 0.f && rr < 3e38f)) val = dihedral_degenerate(x1, x2, cv, sv);
-                                finish_one(r, 4, c, i & 1, val, cv, sv, out + (size_t)i * row_stride);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();  // the records are rewritten by the next quad
-        };
 
         // ---- main loop over the segment's frame blocks (32-bit counters and running pointers: this code runs once
         // per stage and warp)
@@ -554,9 +283,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
                     float* vq = vstage + vq_first;
                     int left = kk - 4 * fli;                                  // frames from this warp's quad on
                     for (; left > 0; left -= 4 * fl) {
-                        const int nvalid = min(4, left);
-                        frames_done += nvalid;
-                        do_quad(fq, reinterpret_cast<const float*>(tq), vq, nvalid);
+                        tw.quad(tabs, lane, fq, (uint32_t)q.slot_bytes, reinterpret_cast<const float*>(tq), vq, min(4, left));
                         fq += fq_step;
                         tq += tq_step;
                         vq += vq_step;
@@ -573,75 +300,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
                 }
             }
         }
-
-        // ---- segment epilogue: per-lane float32 sums -> per-Bond float64 sums of the segment in a fixed order (no
-        // floating-point atomics inside the CTA, so its contribution does not depend on scheduling); segments are then
-        // combined with float64 atomics.  Two rounds of two chunks each; the scratch lives where the edge records were.
-        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // of the slots this warp reduces: sl = warp, warp + 7, ...
-        constexpr int kHalf = 2 * kConsumers;
-#pragma unroll
-        for (int round = 0; round < 2; ++round) {
-            asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");   // main loop (or previous round) is over
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const Role& r = role[2 * round + cc];
-                const int i = cc * kConsumers + tid;
-                float a, b;
-                unpack2(r.s1, a, b);
-                eacc[0 * kHalf + i] = a + b;
-                unpack2(r.s2, a, b);
-                eacc[1 * kHalf + i] = a + b;
-                unpack2(r.c, a, b);
-                eacc[2 * kHalf + i] = a + b;
-                unpack2(r.s, a, b);
-                eacc[3 * kHalf + i] = a + b;
-                ecnt[i] = (working && r.slot >= 0) ? frames_done : 0;
-            }
-            asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
-            // one warp per Bond slot: lane-strided sums over the slot's lane-roles (and their copies in the warps that
-            // share the group), then a fixed butterfly
-            for (int sl = warp; sl < tile.nslots; sl += kWarps) {
-                const int p0 = slist[sl], p1 = slist[sl + 1];
-                const uint16_t* ent = slist + tile.nslots + 1;
-                double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                for (int p = p0 + lane; p < p1; p += 32) {
-                    const int e = ent[p];
-                    const int c = e / kConsumers;
-                    if ((c >> 1) != round) continue;
-                    const int base = e - 2 * round * kConsumers;
-                    for (int j = 0; j < fl; ++j) {
-                        const int i = base + j * ng * 32;      // the same lane-role in the warp that is j frame lanes on
-                        const int cnt = ecnt[i];
-                        if (cnt == 0) continue;
-                        a6[0] += (double)(cnt - (int)snbad[i + 2 * round * kConsumers]);
-                        a6[1] += (double)eacc[0 * kHalf + i];
-                        a6[2] += (double)eacc[1 * kHalf + i];
-                        a6[3] += (double)eacc[2 * kHalf + i];
-                        a6[4] += (double)eacc[3 * kHalf + i];
-                        a6[5] += (double)cnt;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) a6[k] += __shfl_down_sync(0xffffffffu, a6[k], o);
-                }
-                if (lane == 0) {
-                    double* dst = q.partials + (size_t)sbond[sl] * CGB_NPART;
-                    const int where[6] = {0, 1, 2, 3, 4, 6};
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        if (a6[k] != 0.0) atomicAdd(dst + where[k], a6[k]);
-                }
-            }
-        }
-        (void)acc;
-        if (do_hist) {
-            for (int i = tid; i < tile.nslots * nbins; i += kConsumers) {
-                const unsigned int v = shist[i];
-                if (v) atomicAdd(q.hist + (size_t)sbond[i / nbins] * nbins + (i % nbins), (double)v);
-            }
-        }
+        tw.epilogue(tabs, tile, working, warp, lane, kWarps, ng, fl, 1);
     }
 }
 
@@ -650,9 +309,10 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
 // ---------------------------------------------------------------------------------------------- C ABI
 extern "C" int cgb_measure_plan_size(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3,
                                      int64_t n4, int64_t n_beads, int32_t max_span, int32_t max_slots,
-                                     int32_t shape, CgbMeasPlanInfo* info) {
-    if (!info) return CGB_EINVAL;
-    cgb::plan::Compiler cc{col_beads, col_bond, n2, n3, n4, n_beads, max_span, max_slots, shape, nullptr, {}, {}};
+                                     int32_t shape, int32_t unit_groups, CgbMeasPlanInfo* info) {
+    if (!info || unit_groups < 0 || unit_groups > CGB_MEAS_WARPS) return CGB_EINVAL;
+    cgb::plan::Compiler cc{col_beads, col_bond, n2, n3, n4, n_beads, max_span, max_slots, shape, unit_groups, nullptr,
+                           nullptr, {}, {}};
     const int rc = cc.run();
     if (rc != CGB_OK) return rc;
     info->n_tiles = (int64_t)cc.out.tiles.size();
@@ -671,12 +331,15 @@ extern "C" int cgb_measure_plan_size(const int32_t* col_beads, const int32_t* co
 
 extern "C" int cgb_measure_plan_build(const int32_t* col_beads, const int32_t* col_bond, int64_t n2, int64_t n3,
                                       int64_t n4, int64_t n_beads, int32_t max_span, int32_t max_slots,
-                                      int32_t shape, CgbMeasTile* tiles, CgbMeasGroup* groups, CgbMeasLane* lanes,
-                                      int32_t* tile_bonds, uint16_t* tile_lists, int32_t* col_out,
-                                      int64_t* wide_cols) {
+                                      int32_t shape, int32_t unit_groups, CgbMeasTile* tiles, CgbMeasGroup* groups,
+                                      CgbMeasLane* lanes, int32_t* tile_bonds, uint16_t* tile_lists, int32_t* col_out,
+                                      int64_t* wide_cols, uint8_t* tile_start) {
     const int64_t M = n2 + n3 + n4;
     if (M > 0 && !col_out) return CGB_EINVAL;
-    cgb::plan::Compiler cc{col_beads, col_bond, n2, n3, n4, n_beads, max_span, max_slots, shape, col_out, {}, {}};
+    if (unit_groups < 0 || unit_groups > CGB_MEAS_WARPS) return CGB_EINVAL;
+    if (tile_start) std::memset(tile_start, 0, (size_t)std::max<int64_t>(n_beads, 0));
+    cgb::plan::Compiler cc{col_beads, col_bond, n2, n3, n4, n_beads, max_span, max_slots, shape, unit_groups, tile_start,
+                           col_out, {}, {}};
     const int rc = cc.run();
     if (rc != CGB_OK) return rc;
     const auto& o = cc.out;

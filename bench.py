@@ -17,15 +17,22 @@ N = 156,672 atoms -> B = 13,824 MARTINI beads, 10,000 frames, synthetic coordina
                  F*(12N + 12B + 12) per launch / CUDA-event duration, against MEASURED_PEAKS.json.
 * ``cpu_baseline`` the oracle (NumPy restatement of the reference, its loop structure kept) timed on
                  the host cores on a bounded frame sample.
-* ``measure``    supplementary: bonded-term measurement (K2) on config S3 (1 M frames, 66 terms);
-                 ``measure_membrane``: the same on a quarter-size S5 membrane; ``ingest``: compressed
-                 .xtc image -> GPU decode -> mapping -> beads on the host.
+* ``secondary``  the other half of BASELINE.json's metric, bond-measures/s: K2 (one ``measure_fused_kernel`` launch
+                 for all kinds) on config S3 (1 M frames, 66 terms) with its own ``roofline``, ``cpu_baseline``
+                 (oracle bonds.measure + invert) and ``e2e`` (``BondSet.apply`` + ``boltzmann_invert`` from a pinned
+                 host CG trajectory); ``measure_membrane``: the same kernel on a quarter-size S5 membrane.
+* ``pipeline``   SURVEY 8f-1: mapping + measurement as ONE kernel (``cgb_map_measure``) against K1 then K2.
+* ``north_star_s5`` BASELINE.json configs[4]: S5 (20 M atoms) map + bond statistics, frames sharded over the
+                 ranks, ONE NCCL all-reduce of the packed [moments | histograms] buffer and the Boltzmann epilogue
+                 inside the timed step; strong (512 frames in total) and weak (256 frames per GPU) scaling.
+* ``ingest``     compressed .xtc image -> GPU decode -> mapping -> beads on the host.
 
 Multi-GPU (torchrun, one rank per GPU): frames are independent, so every rank maps its own
 10,000-frame shard with no data-path collective (weak scaling); value = all atom-frames / max time.
 """
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -52,6 +59,8 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=2048)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / e2e / measure legs")
     ap.add_argument("--ref-frames-per-worker", type=int, default=128)
+    ap.add_argument("--legs", default="", help="comma list of supplementary legs: cpu,measure,membrane,pipeline,ingest,northstar")
+    ap.add_argument("--northstar-scale", type=float, default=1.0, help="size of the S5 system of the north-star leg")
     return ap.parse_args()
 
 
@@ -153,6 +162,43 @@ def _oracle_map_chunk(args):
     return dt, float(cg.xyz[0, 0, 0])
 
 
+def _oracle_bonds_chunk(args):
+    """Worker of the reference arm, stage 2 + 3: oracle bonds.measure + invert on one block of S3 frames."""
+    map_path, bnd_path, residues, seed_sys, first, count = args
+    from oracle import bonds as obonds, mapping as omap, system as osystem
+    xyz = seed_sys.coordinates_host(count, first_frame=first)
+    box = seed_sys.box_vectors(count, first_frame=first)
+    ocg = omap.apply(omap.parse_map(map_path), osystem.from_residue_lists(residues, xyz, box))
+    terms = obonds.parse_bnd(bnd_path)
+    t0 = time.perf_counter()
+    obonds.measure(terms, ocg)
+    obonds.invert(terms)
+    dt = time.perf_counter() - t0
+    return dt, sum(len(t.indices) for mol in terms.values() for t in mol)
+
+
+def reference_bonds_leg(pool, cores, frames_per_worker=4096):
+    """bond-measures/s of the reference algorithm (oracle port) on all host cores: S3 frames split over workers."""
+    from workloads import synth
+    sysm = synth.small_molecule()
+    map_path, bnd_path = sysm.write_files()
+    residues = oracle_residue_lists(sysm.topology)
+    best = None
+    for rep in range(2):
+        jobs = [(str(map_path), str(bnd_path), residues, sysm, (rep * cores + w) * frames_per_worker, frames_per_worker)
+                for w in range(cores)]
+        results = pool.map(_oracle_bonds_chunk, jobs)
+        slowest = max(r[0] for r in results)
+        best = slowest if best is None else min(best, slowest)
+    n_terms = results[0][1]
+    sample = (f"{cores * frames_per_worker} frames ({frames_per_worker} per worker x {cores} workers) of the "
+              f"1,048,576-frame S3 config, oracle bonds.measure + invert")
+    value = cores * frames_per_worker * n_terms / best
+    return {"metric": "bond-measures/s", "value": value, "unit": "bond-measures/s",
+            "cpu_baseline": {"value": value, "unit": "bond-measures/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "bond-measures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU algorithm (oracle port -- mdtraj cannot be installed, so
     the reference itself cannot be imported) on the host cores, all of them, bounded frame sample."""
@@ -180,6 +226,12 @@ def run_reference(args):
             if step >= args.warmup:
                 times.append(slowest)
             del wall
+        secondary = None
+        if not args.no_extras:
+            try:
+                secondary = reference_bonds_leg(pool, cores)
+            except Exception as exc:  # noqa: BLE001 -- the headline line must still be printed
+                secondary = {"error": repr(exc)}
     units = cores * per_worker * sysm.n_atoms
     total = sum(times)
     value = units * len(times) / total
@@ -194,6 +246,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "atom-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if secondary is not None:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
 
 
@@ -216,23 +270,50 @@ def cpu_baseline_leg(sysm, map_path, frames_total, sample_frames=512):
                       f"best of 2, host has {os.cpu_count()} cores"}
 
 
-def measure_leg(dev, peak_gbs, workload="s3"):
-    """Supplementary: K2 (bond measurement + statistics), device resident, on config S3 or on a
-    quarter-size S5 membrane (many instances per Bond, tiles of 224 columns).
+def _bonds_cpu_baseline(sysm, map_path, bnd_path, frames_total, sample_frames):
+    """Single-threaded oracle for stage 2 + 3: bonds.measure (the mdtraj kernels restated in NumPy) and the
+    statistics / Boltzmann inversion of the reference (bondset.py:496-539, util.py:24-53) on a frame sample."""
+    from oracle import bonds as obonds, mapping as omap, system as osystem
+    residues = oracle_residue_lists(sysm.topology)
+    xyz = sysm.coordinates_host(sample_frames)
+    box = sysm.box_vectors(sample_frames)
+    ocg = omap.apply(omap.parse_map(map_path), osystem.from_residue_lists(residues, xyz, box))
+    terms = obonds.parse_bnd(bnd_path)
+    t0 = time.perf_counter()
+    obonds.measure(terms, ocg)
+    obonds.invert(terms)
+    dt = time.perf_counter() - t0
+    n_terms = sum(len(t.indices) for mol in terms.values() for t in mol)
+    return {"value": sample_frames * n_terms / dt, "unit": "bond-measures/s", "cores": 1, "kind": "port",
+            "sample": f"{sample_frames} of {frames_total} frames, oracle bonds.measure + invert, single thread, "
+                      f"host has {os.cpu_count()} cores"}
 
-    `value` times the three `measure_kernel` launches of one `cgb_measure` call (values + moments +
-    circular sums + 128-bin histograms); `api_ms_per_pass` is `BondSet.apply` as a user calls it
-    (adds buffer allocation and the one-frame shift pre-pass)."""
+
+def _k2_traffic(workload, n_frames):
+    """DRAM bytes of one K2 launch from the committed ncu capture (per frame, scaled to this run), or None."""
+    path = ROOT / "profiles" / "k2_traffic.json"
+    try:
+        tr = json.loads(path.read_text())[workload]
+        return tr["dram_bytes_per_frame"] * n_frames, tr.get("source")
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def measure_leg(dev, peak_gbs, workload="s3", with_cpu=True, with_e2e=True):
+    """Stage 2 (K2, one cgb_measure_fused launch for all kinds): device resident, on config S3 or on a quarter-size
+    S5 membrane.  `value` = values + moments + circular sums + 128-bin histograms in one pass; `stats_only` = the
+    same without writing the values; `e2e` = BondSet.apply + boltzmann_invert from a pinned HOST CG trajectory."""
+    import numpy as np
     import torch
     from pycgtool_b200 import BondSet, Frame, Mapping, _lib, device
     from workloads import synth
     from workloads.synth import Options
-    lib = _lib.load()
+    _lib.load()
     if workload == "s3":
-        sysm, n_frames, chunk = synth.small_molecule(), 1 << 20, 1 << 16
+        sysm, n_frames, chunk, cpu_frames = synth.small_molecule(), 1 << 20, 1 << 16, 1 << 15
         label = "S3 small molecule: 24 beads, 66 terms (23 bonds, 22 angles, 21 dihedrals), 1,048,576 frames"
     else:
-        sysm, n_frames, chunk = synth.s5(scale=0.25), 256, 8
+        sysm, n_frames, chunk, cpu_frames = synth.s5(scale=0.25), 256, 8, 1
         label = "quarter-size S5 membrane (5M atoms), 256 frames"
     map_path, bnd_path = sysm.write_files()
     xyz = sysm.coordinates_device(n_frames, dev, chunk=chunk)
@@ -253,39 +334,228 @@ def measure_leg(dev, peak_gbs, workload="s3"):
     st = bonds._state
     plan = st.plan
     n2, n3, n4 = plan.counts
+    n_terms = n2 + n3 + n4
+    measures = n_frames * n_terms
+    touched = len(np.unique(plan.col_beads))
 
-    def kernels():
-        st.packed.zero_()
-        bonds._launch_measure(plan, st.source, n_frames, st.shift, st.values, st.packed, 128, st.hist_lo, st.hist_hi)
+    def timed(values, nbins):
+        def launch():
+            st.packed.zero_()
+            bonds._launch_measure(plan, st.source, n_frames, st.shift, values, st.packed, nbins,
+                                  st.hist_lo, st.hist_hi)
+        for _ in range(2):
+            launch()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(reps):
+            launch()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / reps
 
-    for _ in range(2):
-        kernels()
-    torch.cuda.synchronize()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for _ in range(reps):
-        kernels()
-    stop.record()
-    torch.cuda.synchronize()
-    ms = start.elapsed_time(stop) / reps
+    ms = timed(st.values, 128)
+    ms_stats = timed(None, 128)
     t0 = time.perf_counter()
     bonds.boltzmann_invert()
     torch.cuda.synchronize()
     invert_ms = 1e3 * (time.perf_counter() - t0)
-    n_terms = n2 + n3 + n4
-    measures = n_frames * n_terms
-    import numpy as np
-    touched = len(np.unique(plan.col_beads))
-    bytes_alg = n_frames * (12 * touched + 4 * n_terms + 36)   # 12 B per bead touched
+    bytes_alg = n_frames * (12 * touched + 4 * n_terms + 36)   # 12 B per bead touched + 4 B per measure
+    bytes_stats = n_frames * (12 * touched + 36)
     gbs = bytes_alg / (ms * 1e-3) / 1e9
+    traffic, traffic_src = _k2_traffic(workload, n_frames)
     if workload != "s3":
         label += f": {plan.n_beads:,} beads, {n_terms:,} terms per frame ({n2:,} bonds, {n3:,} angles, {n4:,} dihedrals)"
-    return {"workload": label,
-            "value": measures / (ms * 1e-3), "unit": "bond-measures/s", "ms_per_pass": ms,
-            "includes": "values + moments + circular sums + 128-bin histograms, ONE measure_fused_kernel launch for all kinds",
-            "api_ms_per_pass": api_ms, "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs,
-            "frac_of_hbm_peak": gbs / peak_gbs, "bound": "instruction issue (atan2 / histogram per measure), not HBM",
-            "boltzmann_invert_ms": invert_ms}
+    leg = {"metric": "bond-measures/s", "value": measures / (ms * 1e-3), "unit": "bond-measures/s",
+           "ms_per_step": ms, "dtype": "f32", "config": {"workload": label},
+           "includes": "values + moments + circular sums + 128-bin histograms, ONE measure_fused_kernel launch "
+                       "for all kinds",
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                        "traffic": traffic, "traffic_source": traffic_src, "kernel": "cgb::measure_fused_kernel",
+                        "algorithmic_bytes_per_launch": bytes_alg, "frac_of_nominal_8TBs": gbs / 8000.0,
+                        "limiter": "instruction issue (minimum image, atan2, statistics and histogram per "
+                                   "measure), not DRAM"},
+           "stats_only": {"value": measures / (ms_stats * 1e-3), "ms_per_step": ms_stats,
+                          "algorithmic_bytes_per_launch": bytes_stats,
+                          "achieved_gbs": bytes_stats / (ms_stats * 1e-3) / 1e9},
+           "api_ms_per_pass": api_ms, "boltzmann_invert_ms": invert_ms, "gpu_launches_per_step": 1}
+    if with_e2e:
+        # e2e: the CG trajectory starts in pinned host memory; H2D, K2, the epilogue and the D2H of the fitted
+        # parameters are inside the timed region (BondSet.apply + boltzmann_invert as a user calls them)
+        ef = n_frames if workload == "s3" else min(n_frames, 128)
+        host = torch.empty((ef, plan.n_beads, 3), dtype=torch.float32, pin_memory=True)
+        host.copy_(cg._trajectory.device_xyz()[:ef])
+        torch.cuda.synchronize()
+        hframe = Frame.from_arrays(cg._topology, host.numpy(), unitcell_vectors=box[:ef])
+
+        def e2e_step():
+            hframe._trajectory.drop_device()
+            bonds.apply(hframe, store_values=False)
+            bonds.boltzmann_invert()
+            return bonds
+
+        for _ in range(2):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        leg["e2e"] = {"value": ef * n_terms / dt, "unit": "bond-measures/s", "ms_per_step": dt * 1e3,
+                      "h2d_bytes_per_step": int(host.numel() * 4 + ef * 36),
+                      "d2h_bytes_per_step": int(plan.n_bonds * (8 * 5 + 8 * 128)), "frames_per_step": ef,
+                      "note": "BondSet.apply(store_values=False) + boltzmann_invert on a pinned host CG trajectory: "
+                              "H2D -> K2 -> epilogue -> D2H of parameters and histograms; PCIe-bound"}
+        del host, hframe
+    if with_cpu:
+        leg["cpu_baseline"] = _bonds_cpu_baseline(sysm, map_path, bnd_path, n_frames, cpu_frames)
+    return leg
+
+
+def pipeline_leg(dev, peak_gbs, frames=64):
+    """mapping + measurement in ONE kernel (cgb_map_measure) on a quarter-size S5 membrane, against the
+    two separate launches (K1 then K2) on the same inputs.  Bytes: 12 N + 12 B + 4 M + 48 per frame."""
+    import numpy as np
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, map_and_measure, pipeline
+    from workloads import synth
+    from workloads.synth import Options
+    sysm = synth.s5(scale=0.25)
+    map_path, bnd_path = sysm.write_files()
+    xyz = sysm.coordinates_device(frames, dev, chunk=8)
+    box = sysm.box_vectors(frames)
+    mapper, bonds, bonds2 = Mapping(map_path, Options()), BondSet(bnd_path, Options()), BondSet(bnd_path, Options())
+    frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
+    cg = map_and_measure(mapper, bonds, frame)
+    map_plan = mapper._plan_for(frame._topology)
+    fused = pipeline._fused_plan(mapper, bonds, map_plan) is not None
+    st = bonds._state
+    plan = st.plan
+    n_terms, n_atoms, n_beads = plan.n_cols, sysm.n_atoms, plan.n_beads
+    reps = 5
+
+    def run(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(reps):
+            fn()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / reps
+
+    def fused_step():
+        st.packed.zero_()
+        st.relaunch()
+
+    ms_fused = run(fused_step) if fused else None
+    lengths = torch.from_numpy(np.ascontiguousarray(np.stack([box[:, 0, 0], box[:, 1, 1], box[:, 2, 2]], axis=1))).to(dev)
+    out = cg._trajectory.device_xyz()
+    bonds2.apply(cg)
+    st2 = bonds2._state
+
+    def separate_step():
+        mapper.map_device(map_plan, xyz, lengths, out=out)
+        st2.packed.zero_()
+        bonds2._launch_measure(st2.plan, st2.source, frames, st2.shift, st2.values, st2.packed, 128,
+                               st2.hist_lo, st2.hist_hi)
+
+    ms_sep = run(separate_step)
+    bytes_alg = frames * (12 * n_atoms + 12 * n_beads + 4 * n_terms + 48)
+    ms = ms_fused if fused else ms_sep
+    return {"what": "Mapping.apply + BondSet.apply as one pass over the atoms (map_and_measure): beads written once, "
+                    "never re-read; values + statistics + histograms in the same kernel",
+            "workload": f"quarter-size S5 membrane: {n_atoms:,} atoms -> {n_beads:,} beads, {n_terms:,} terms, {frames} frames",
+            "fused_kernel": fused, "ms_per_step": ms, "separate_k1_k2_ms": ms_sep,
+            "atom_frames_per_s": frames * n_atoms / (ms * 1e-3), "bond_measures_per_s": frames * n_terms / (ms * 1e-3),
+            "algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": bytes_alg / (ms * 1e-3) / 1e9 / peak_gbs,
+            "separate_achieved_gbs": (bytes_alg + frames * 12 * len(np.unique(plan.col_beads))) / (ms_sep * 1e-3) / 1e9}
+
+
+def north_star_leg(dev, peak_gbs, world, rank, td, mode, scale=1.0):
+    """BASELINE.json configs[4]: S5 (20 M atoms), full map + bond statistics, frames sharded over the ranks, the
+    per-Bond moments and histograms combined by ONE NCCL all-reduce of the packed buffer (cgb_allreduce_partials).
+    A step = map_and_measure (fused K1+K2) -> all-reduce -> Boltzmann epilogue -> fitted parameters on the host:
+    everything, the collective included, inside the timed region.  mode 'strong': 512 frames in total;
+    'weak': 256 frames per GPU."""
+    import numpy as np
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, dist, map_and_measure
+    from workloads import synth
+    from workloads.synth import Options
+    sysm = synth.s5(scale=scale)
+    total = 512 if mode == "strong" else 256 * world
+    f0, f1 = dist.frame_shard(total, rank, world)
+    frames = f1 - f0
+    need = frames * (sysm.n_atoms * 12 + 2_000_000 * 12 * scale + 800_000 * 4 * scale) + (4 << 30)
+    free = torch.cuda.mem_get_info(dev)[0]
+    ok = torch.tensor([1 if need < free else 0], device=dev)
+    if world > 1:
+        td.all_reduce(ok, op=td.ReduceOp.MIN)
+    if not int(ok.item()):
+        return {"skipped": f"{mode}: {frames} frames per rank need {need / 1e9:.0f} GB, {free / 1e9:.0f} GB free"}
+    map_path, bnd_path = sysm.write_files()
+    xyz = sysm.coordinates_device(frames, dev, first_frame=f0, chunk=4)
+    box = sysm.box_vectors(frames, first_frame=f0)
+    mapper, bonds = Mapping(map_path, Options()), BondSet(bnd_path, Options())
+    frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
+
+    def step():
+        map_and_measure(mapper, bonds, frame, store_values=False)
+        bonds.boltzmann_invert()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize()
+    reps = 5
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        step()
+    stop.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([start.elapsed_time(stop) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms = float(t.item())
+    # the kernel alone on this rank, and the collective alone (warm)
+    st = bonds._state
+    start.record()
+    for _ in range(reps):
+        st.packed.zero_()
+        st.relaunch()
+    stop.record()
+    torch.cuda.synchronize()
+    kernel_ms = start.elapsed_time(stop) / reps
+    scratch = torch.zeros_like(st.packed)
+    for _ in range(5):
+        dist.allreduce_packed(scratch)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(20):
+        dist.allreduce_packed(scratch)
+    stop.record()
+    torch.cuda.synchronize()
+    coll_us = 1e3 * start.elapsed_time(stop) / 20
+    plan = st.plan
+    n_terms, n_atoms = plan.n_cols, sysm.n_atoms
+    bytes_alg = frames * (12 * n_atoms + 12 * plan.n_beads + 48)
+    return {"workload": f"S5 x{scale:g}: {n_atoms:,} atoms -> {plan.n_beads:,} beads, {n_terms:,} terms per frame, "
+                        f"{plan.n_bonds} Bonds; {total} frames over {world} GPU(s) ({frames} on this rank)",
+            "scaling": mode, "step": "map_and_measure (fused K1+K2, stats-only) -> NCCL all-reduce of "
+                                     "[moments | histograms] -> Boltzmann epilogue -> parameters on the host",
+            "ms_per_step": ms, "atom_frames_per_s": total * n_atoms / (ms * 1e-3),
+            "bond_measures_per_s": total * n_terms / (ms * 1e-3), "kernel_ms": kernel_ms,
+            "kernel_achieved_gbs": bytes_alg / (kernel_ms * 1e-3) / 1e9,
+            "kernel_frac_of_hbm_peak": bytes_alg / (kernel_ms * 1e-3) / 1e9 / peak_gbs,
+            "allreduce_warm_us": coll_us, "allreduce_bytes": int(st.packed.numel() * 8),
+            "collective_inside_timed_region": True}
 
 
 def ingest_leg(sysm, mapper, plan, dev, frames=2048):
@@ -511,42 +781,57 @@ def run_b200(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    legs = set(args.legs.split(",")) if args.legs else {"cpu", "measure", "membrane", "pipeline", "ingest", "northstar"}
+    if not args.no_extras:
+        del xyz, out
+        torch.cuda.empty_cache()
+
+    def guarded(name, fn):
+        """A supplementary leg must not take the headline down; with several ranks every rank still enters it."""
+        try:
+            return fn()
+        except Exception as exc:  # noqa: BLE001
+            if world > 1:
+                raise
+            return {"error": f"{name}: {exc!r}"}
+
     if rank == 0 and world == 1 and not args.no_extras:
-        del xyz, out
-        torch.cuda.empty_cache()
-        line["cpu_baseline"] = cpu_baseline_leg(sysm, map_path, frames)
-        try:
-            line["measure"] = measure_leg(dev, peak_gbs)
-            line["measure_membrane"] = measure_leg(dev, peak_gbs, "membrane")
-        except Exception as exc:  # supplementary leg must not take the headline down
-            line["measure"] = {"error": repr(exc)}
-        if args.workload == "s2":
-            try:
-                torch.cuda.empty_cache()
-                line["ingest"] = ingest_leg(sysm, mapper, plan, dev)
-            except Exception as exc:
-                line["ingest"] = {"error": repr(exc)}
-    if world > 1 and not args.no_extras:
-        # bond-measures/s at N GPUs (weak scaling): every rank measures its own 1,048,576-frame S3 shard; the
-        # shift broadcast and the all-reduce of the partial moments / histograms (NCCL) run inside BondSet
-        del xyz, out
-        torch.cuda.empty_cache()
-        leg, ms = None, float("inf")
-        try:
-            leg = measure_leg(dev, peak_gbs)
-            ms = leg["ms_per_pass"]
-        except Exception as exc:  # noqa: BLE001 -- keep the ranks in step: the reduction below still runs
-            leg = {"error": repr(exc)}
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if "cpu" in legs:
+            line["cpu_baseline"] = cpu_baseline_leg(sysm, map_path, frames)
+        if "measure" in legs:
+            line["secondary"] = guarded("measure", lambda: measure_leg(dev, peak_gbs))
+        if "membrane" in legs:
+            torch.cuda.empty_cache()
+            line["measure_membrane"] = guarded("membrane", lambda: measure_leg(dev, peak_gbs, "membrane", with_cpu=False))
+        if "pipeline" in legs:
+            torch.cuda.empty_cache()
+            line["pipeline"] = guarded("pipeline", lambda: pipeline_leg(dev, peak_gbs))
+        if "ingest" in legs and args.workload == "s2":
+            torch.cuda.empty_cache()
+            line["ingest"] = guarded("ingest", lambda: ingest_leg(sysm, mapper, plan, dev))
+    if world > 1 and not args.no_extras and "measure" in legs:
+        # bond-measures/s at N GPUs (weak scaling): every rank measures its own 1,048,576-frame S3 shard (kernel
+        # only; the collective is measured inside the north-star leg below)
+        leg = measure_leg(dev, peak_gbs, with_cpu=False, with_e2e=False)
+        t = torch.tensor([leg["ms_per_step"]], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        if "error" not in leg and math.isfinite(float(t.item())):
-            per_rank = leg["value"] * leg["ms_per_pass"] * 1e-3
-            leg["ms_per_pass"] = float(t.item())
-            leg["value"] = world * per_rank / (leg["ms_per_pass"] * 1e-3)
-            leg["scaling"] = "weak: one 1,048,576-frame shard per rank, max time over ranks"
-            for key in ("achieved_gbs", "frac_of_hbm_peak", "algorithmic_bytes"):
-                leg.pop(key, None)
-        line["measure"] = leg
+        per_rank = leg["value"] * leg["ms_per_step"] * 1e-3
+        leg["ms_per_step"] = float(t.item())
+        leg["value"] = world * per_rank / (leg["ms_per_step"] * 1e-3)
+        leg["scaling"] = "weak: one 1,048,576-frame shard per rank, max kernel time over ranks, no collective"
+        leg.pop("roofline", None)
+        leg.pop("stats_only", None)
+        line["secondary"] = leg
+    if not args.no_extras and "northstar" in legs:
+        # BASELINE.json configs[4] at this N: every rank takes part (collective inside the timed region)
+        torch.cuda.empty_cache()
+        ns = {}
+        for mode in ("strong", "weak"):
+            gc.collect()                     # BondSet <-> state reference cycles hold the previous leg's trajectory
+            torch.cuda.empty_cache()
+            ns[mode] = guarded("northstar " + mode,
+                               lambda m=mode: north_star_leg(dev, peak_gbs, world, rank, td, m, args.northstar_scale))
+        line["north_star_s5"] = ns
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -181,14 +181,16 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
                                          device.dptr(d["bond_first"]), device.dptr(d["natoms_measured"]),
                                          plan.n_bonds, device.dptr(shift), stream), "cgb_measure_shift")
     dist.broadcast_device(shift, src=0)
-    if n_frames:
+
+    def launch(packed_=packed, values_=values):
+        """One pass of the fused kernel (+ the virtual beads) into the given accumulators; bench.py times this."""
         _lib.check(lib.cgb_map_measure(
             device.dptr(xyz), device.dptr(box_len), device.dptr(box_vec), ortho, n_frames, map_plan.n_atoms,
             map_plan.n_beads, device.dptr(d_fused["tiles"]), fp.n_tiles, device.dptr(d_fused["entries"]), fp.max_span,
             fp.max_ent, FUSED_TILE_BEADS, device.dptr(out), device.dptr(d_fused["meas_of_tile"]),
             device.dptr(d["tiles"]), device.dptr(d["groups"]), device.dptr(d["lanes"]), device.dptr(d["tile_bonds"]),
-            device.dptr(d["tile_lists"]), plan.shape, plan.max_slots, device.dptr(shift), device.dptr(values), n_cols,
-            device.dptr(packed[:npart]), device.dptr(packed[npart:] if nbins else None), device.dptr(hist_lo),
+            device.dptr(d["tile_lists"]), plan.shape, plan.max_slots, device.dptr(shift), device.dptr(values_), n_cols,
+            device.dptr(packed_[:npart]), device.dptr(packed_[npart:] if nbins else None), device.dptr(hist_lo),
             device.dptr(hist_hi), nbins, stream), "cgb_map_measure")
         if d_map["n_virt"]:
             # virtual beads read the CG frame, after the real beads (mapping.py:431-438)
@@ -198,12 +200,16 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
                                           device.dptr(d_map["virt_list"]), d_map["n_virt"], device.dptr(out), stream),
                        "cgb_map_gather")
 
+    if n_frames:
+        launch()
+
     cg = Frame.from_arrays(map_plan.cg_topology, xyz=None, unitcell_vectors=traj.unitcell_vectors, time=frame.time,
                            xyz_device=out)
     bondset._state = None
     state = _MeasureState(bondset, plan, n_frames, values, packed, nbins, shift, hist_lo, hist_hi, dev,
                           (out, box_vec, ortho))
     state.hist_lo_host, state.hist_hi_host = lo, hi
+    state.relaunch = launch
     bondset._state = state
     for bond_id, bond in enumerate(itertools.chain(*bondset._molecules.values())):
         bond._values = None

@@ -338,6 +338,12 @@ class Trajectory:
             self._xyz_dev = dev.to_device(self._xyz, device)
         return self._xyz_dev
 
+    def drop_device(self):
+        """Forget the device copies (the host copy stays): the next use uploads again."""
+        if self._xyz is not None:
+            self._xyz_dev = None
+        self._vectors_dev = None
+
     def device_box_vectors(self, device):
         """(F, 9) float32 box vectors on the device (uploaded once), or None without a unit cell."""
         if self._vectors is None:

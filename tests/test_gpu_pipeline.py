@@ -157,4 +157,5 @@ def test_unsupported_systems_fall_back_to_two_stages(options):
     b.boltzmann_invert()
     for x, y in zip(a["MOL"], b["MOL"]):
         assert np.array_equal(np.asarray(x.values), np.asarray(y.values))
-        assert x.eqm == y.eqm and x.fconst == y.fconst
+        # float64 sums of different CTAs meet in global atomics: the last bits depend on their order
+        assert x.eqm == pytest.approx(y.eqm, rel=1e-9) and x.fconst == pytest.approx(y.fconst, rel=1e-9)

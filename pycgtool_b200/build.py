@@ -24,7 +24,7 @@ STAMP = CSRC / ".build_stamp"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl", "--threads", "0",
 ]
 
 

@@ -47,7 +47,7 @@ struct MMParams {
     int32_t cg_frame_bytes;       // bytes between the frames of a CG-tile slot (multiple of 16)
     int32_t cg_slot_bytes;        // one slot: four frames + their box table
     // shared-memory map of the measurement region (byte offsets from the start of shared memory)
-    int32_t off_bars, off_sbond, off_sparam, off_shist, off_lists, off_nbad, off_eacc, off_ecache, off_cg;
+    int32_t off_bars, off_sbond, off_sparam, off_shist, off_lists, off_nbad, off_eacc, off_roles, off_ecache, off_cg;
 };
 
 template <bool HAS_BOX, int MIC, int SHAPE>
@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(256, 2) map_measure_kernel(const MapParams p, 
     tabs.eacc = reinterpret_cast<float*>(smem_raw + m.off_eacc);
     tabs.ecnt = reinterpret_cast<int*>(tabs.eacc + 4 * 2 * kTermThreads);
     tabs.shist32 = smem_u32(tabs.shist);
+    tabs.dummy32 = smem_u32(smem_raw + m.off_bars + 56);
+    tabs.rs32 = (uint32_t)m.row_stride;
     tabs.shift = m.shift;
     tabs.hlo = m.hlo;
     tabs.hhi = m.hhi;
@@ -238,7 +240,8 @@ __global__ void __launch_bounds__(256, 2) map_measure_kernel(const MapParams p, 
     const int fli = w / ng;
     term_tables_fill(tabs, mtile, m.tile_bonds, m.tile_lists, vt, kMMWarps * 32);
     TermWarp<MIC, SHAPE> tw;
-    tw.setup(working, m.groups[mtile.group0 + gi], m.lanes + (size_t)(mtile.group0 + gi) * kChunks * 32, lane, 0u, ecache32, vt);
+    tw.setup(working, m.groups[mtile.group0 + gi], m.lanes + (size_t)(mtile.group0 + gi) * kChunks * 32, lane, 0u, ecache32,
+             smem_u32(smem_raw + m.off_roles) + (uint32_t)w * (uint32_t)kRoleTableBytes, vt);
     asm volatile("bar.sync 2, %0;" ::"r"(kMMWarps * 32) : "memory");
     if (working) {
         for (int it = fli; it < nst; it += fl) {
@@ -248,8 +251,15 @@ __global__ void __launch_bounds__(256, 2) map_measure_kernel(const MapParams p, 
             const unsigned char* slot = cgbuf + (size_t)cs * m.cg_slot_bytes;
             float* vq = m.values ? m.values + (size_t)f0 * m.row_stride : nullptr;
             mbar_wait(&cgfull[cs], (it / kMMSlots) & 1);
-            tw.quad(tabs, lane, slot, (uint32_t)m.cg_frame_bytes,
-                    reinterpret_cast<const float*>(slot + (size_t)FG * m.cg_frame_bytes), vq, kk);
+            const float* tq = reinterpret_cast<const float*>(slot + (size_t)FG * m.cg_frame_bytes);
+            // the launch's output options are uniform: one of four specialised copies of the quad runs
+            if (m.values != nullptr) {
+                if (m.hist != nullptr) tw.template quad_mode<3>(tabs, lane, slot, (uint32_t)m.cg_frame_bytes, tq, vq, kk);
+                else tw.template quad_mode<1>(tabs, lane, slot, (uint32_t)m.cg_frame_bytes, tq, vq, kk);
+            } else {
+                if (m.hist != nullptr) tw.template quad_mode<2>(tabs, lane, slot, (uint32_t)m.cg_frame_bytes, tq, vq, kk);
+                else tw.template quad_mode<0>(tabs, lane, slot, (uint32_t)m.cg_frame_bytes, tq, vq, kk);
+            }
             if (lane == 0) mbar_arrive(&cgempty[cs]);
         }
     }
@@ -276,7 +286,7 @@ extern "C" int cgb_map_measure(const float* xyz, const float* box_len, const flo
         !tile_lists || !partials)
         return CGB_EINVAL;
     if (hist && (!hist_lo || !hist_hi || n_bins < 1 || n_bins > 512)) return CGB_EINVAL;
-    if (values && row_stride < 1) return CGB_EINVAL;
+    if (values && (row_stride < 1 || row_stride > 0x3fffffffLL)) return CGB_EINVAL;
     if (shape != CGB_SHAPE_EAD && shape != CGB_SHAPE_EEAA) return CGB_EINVAL;
     if ((reinterpret_cast<uintptr_t>(xyz) & 3u) || (reinterpret_cast<uintptr_t>(cg_xyz) & 3u)) return CGB_EALIGN;
     if (n_tiles > 0x7fffffffLL) return CGB_EINVAL;
@@ -300,7 +310,10 @@ extern "C" int cgb_map_measure(const float* xyz, const float* box_len, const flo
     p.k = kMMFG;                                    // one quad per stage
     p.tab_off = p.k * p.slot_floats;
     p.stage_floats = p.tab_off + ((6 * p.k + 3) & ~3);
+    // frames per CTA: long runs amortise a CTA's start-up (plan entries, first copies), as long as the grid keeps
+    // at least ~16 CTAs per SM to balance the tail
     p.fc = 128;
+    while (p.fc < 512 && n_tiles * ((n_frames + 2 * p.fc - 1) / (2 * p.fc)) >= 16 * 148) p.fc *= 2;
     {
         const int64_t nchunks = (n_frames + p.fc - 1) / p.fc;
         if (nchunks > 65535) {
@@ -349,6 +362,8 @@ extern "C" int cgb_map_measure(const float* xyz, const float* box_len, const flo
     off += (size_t)kRoles * 4;
     m.off_eacc = (int)off;
     off = up(off + (size_t)(4 * 2 * kTermThreads + 2 * kTermThreads) * 4, 128);
+    m.off_roles = (int)off;
+    off += (size_t)kMMWarps * kRoleTableBytes;
     m.off_ecache = (int)off;
     off += (size_t)kMMWarps * (shape == CGB_SHAPE_EAD ? RecLayout<CGB_SHAPE_EAD>::kWarpBytes
                                                       : RecLayout<CGB_SHAPE_EEAA>::kWarpBytes);

@@ -60,7 +60,7 @@ struct FusedParams {
     int32_t contiguous;    // the tile is the whole CG frame: one bulk copy per stage
     int32_t ecache_warp_bytes;
     // shared-memory map (byte offsets)
-    int32_t off_sparam, off_shist, off_lists, off_eacc, off_nbad, off_ecache, off_stages;
+    int32_t off_sparam, off_shist, off_lists, off_eacc, off_nbad, off_roles, off_ecache, off_stages;
 };
 
 // The share of the work items (tile-major, frame-block-minor) of one CTA, cut into segments: consecutive blocks of
@@ -85,13 +85,14 @@ struct Schedule {
     }
 };
 
-template <int MIC, int SHAPE>
+template <int MIC, int SHAPE, int MODE>   // MODE: bit 0 = the values are stored, bit 1 = histograms
 __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const FusedParams q) {
     static_assert(MIC == MIC_ORTHO || MIC == MIC_TRICLINIC, "no box = orthorhombic path with a zero box table");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + kStagesMax;
-    int* sbond = reinterpret_cast<int*>(smem + 128);
+    unsigned int* scratch = reinterpret_cast<unsigned int*>(smem + 64);   // scratch words (hist_add_pair_pred)
+    int* sbond = reinterpret_cast<int*>(smem + 192);
     // per Bond slot of the tile: {-shift, bins / (hi - lo), -lo * that - 0.5, unused} for the statistics / histogram
     float4* sparam = reinterpret_cast<float4*>(smem + q.off_sparam);
     unsigned int* shist = reinterpret_cast<unsigned int*>(smem + q.off_shist);
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     // ---------------------------------------------------------------------- consumer warps
     using Rec = RecLayout<SHAPE>;
     const uint32_t ecache32 = smem_u32(smem + q.off_ecache) + (uint32_t)warp * (uint32_t)Rec::kWarpBytes;
+    const uint32_t table32 = smem_u32(smem + q.off_roles) + (uint32_t)warp * (uint32_t)kRoleTableBytes;
     TermTables tabs;
     tabs.sbond = sbond;
     tabs.sparam = sparam;
@@ -231,6 +233,8 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     tabs.eacc = eacc;
     tabs.ecnt = ecnt;
     tabs.shist32 = smem_u32(shist);
+    tabs.dummy32 = smem_u32(scratch);
+    tabs.rs32 = (uint32_t)q.row_stride;
     tabs.shift = q.shift;
     tabs.hlo = q.hlo;
     tabs.hhi = q.hhi;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     tabs.partials = q.partials;
     tabs.hist = q.hist;
     tabs.nbins = q.nbins;
-    const bool store = q.values != nullptr;  // uniform
+    constexpr bool store = (MODE & 1) != 0;
     const int64_t row_stride = q.row_stride;
     TermWarp<MIC, SHAPE> tw;
     int s = 0;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
         const uint32_t h0 = (uint32_t)(reinterpret_cast<uintptr_t>(q.xyz + (size_t)tile.bead0 * 3) & 15u);
         term_tables_fill(tabs, tile, q.tile_bonds, q.tile_lists, tid, kConsumers);
         tw.setup(working, q.groups[tile.group0 + gi], q.lanes + (size_t)(tile.group0 + gi) * kChunks * 32, lane, h0,
-                 ecache32, tid);
+                 ecache32, table32, tid);
         asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
 
         // ---- main loop over the segment's frame blocks (32-bit counters and running pointers: this code runs once
@@ -267,27 +271,22 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
             int frames_left = (int)min(q.F - f_seg, (int64_t)0x7fffffff);
             float* vstage = store ? q.values + (size_t)f_seg * row_stride : nullptr;
             const size_t vstage_step = (size_t)q.k * row_stride;
-            const uint32_t fq_first = (uint32_t)(4 * fli) * (uint32_t)q.slot_bytes;
-            const uint32_t fq_step = (uint32_t)(4 * fl) * (uint32_t)q.slot_bytes;
-            const uint32_t tq_first = (uint32_t)q.tab_off + (MIC == MIC_ORTHO ? 96u : 192u) * (uint32_t)fli;
-            const uint32_t tq_step = (MIC == MIC_ORTHO ? 96u : 192u) * (uint32_t)fl;
-            const size_t vq_first = (size_t)(4 * fli) * row_stride, vq_step = (size_t)(4 * fl) * row_stride;
+            const uint32_t quad_bytes = 4u * (uint32_t)q.slot_bytes;
+            const uint32_t tq_quad = MIC == MIC_ORTHO ? 96u : 192u;
+            const size_t vq_quad = (size_t)4 * row_stride;
             const unsigned char* stage = stages + (size_t)s * q.stage_bytes;
             for (int it = 0; it < seg_count; ++it) {
                 const int kk = min(q.k, frames_left);
                 frames_left -= q.k;
                 mbar_wait(&full[s], phase);
                 if (working) {
-                    const unsigned char* fq = stage + fq_first;
-                    const unsigned char* tq = stage + tq_first;
-                    float* vq = vstage + vq_first;
-                    int left = kk - 4 * fli;                                  // frames from this warp's quad on
-                    for (; left > 0; left -= 4 * fl) {
-                        tw.quad(tabs, lane, fq, (uint32_t)q.slot_bytes, reinterpret_cast<const float*>(tq), vq, min(4, left));
-                        fq += fq_step;
-                        tq += tq_step;
-                        vq += vq_step;
-                    }
+                    // the warps that share a group take the quads of the stage in turn (a fixed assignment: the float32
+                    // sums of a lane, hence the statistics, do not depend on scheduling)
+                    const int nquads = (kk + 3) >> 2;
+                    for (int qd = fli; qd < nquads; qd += fl)
+                        tw.template quad_mode<MODE>(tabs, lane, stage + (uint32_t)qd * quad_bytes, (uint32_t)q.slot_bytes,
+                                reinterpret_cast<const float*>(stage + (uint32_t)q.tab_off + (uint32_t)qd * tq_quad),
+                                vstage + (size_t)qd * vq_quad, min(4, kk - 4 * qd));
                 }
                 vstage += vstage_step;
                 __syncwarp();
@@ -369,7 +368,7 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
     q.nstage = tune && tune->n_stages ? tune->n_stages : 3;
     if (q.nstage < 2 || q.nstage > kStagesMax) return CGB_EINVAL;
     auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
-    size_t off = 128 + (size_t)((q.max_slots + 3) & ~3) * 4;
+    size_t off = 192 + (size_t)((q.max_slots + 3) & ~3) * 4;
     off = up(off, 16);
     q.off_sparam = (int)off;
     off += (size_t)q.max_slots * 16;
@@ -380,6 +379,8 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
     q.off_eacc = 0;
     q.off_nbad = (int)off;
     off = up(off + (size_t)kRoles * 4, 128);
+    q.off_roles = (int)off;
+    off += (size_t)kWarps * kRoleTableBytes;
     q.off_ecache = (int)off;
     q.ecache_warp_bytes = shape == CGB_SHAPE_EAD ? RecLayout<CGB_SHAPE_EAD>::kWarpBytes : RecLayout<CGB_SHAPE_EEAA>::kWarpBytes;
     off += (size_t)kWarps * q.ecache_warp_bytes;
@@ -446,7 +447,7 @@ extern "C" int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int 
     if (n_frames == 0 || n_tiles == 0) return CGB_OK;
     if (!cg_xyz || !tiles || !groups || !lanes || !tile_bonds || !tile_lists || !partials) return CGB_EINVAL;
     if (hist && (!hist_lo || !hist_hi || n_bins < 1 || n_bins > 512)) return CGB_EINVAL;  // fast-bin error bound
-    if (values && row_stride < 1) return CGB_EINVAL;
+    if (values && (row_stride < 1 || row_stride > 0x3fffffffLL)) return CGB_EINVAL;
     if (shape != CGB_SHAPE_EAD && shape != CGB_SHAPE_EEAA) return CGB_EINVAL;
     if (max_span < 1 || max_slots < 1 || max_edge_chunks < 1 || max_edge_chunks > CGB_MEAS_EDGE_CHUNKS ||
         n_tiles > 0x7fffffffLL)
@@ -484,17 +485,26 @@ extern "C" int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int 
     if (rc != CGB_OK) return rc;
     const bool triclinic = box_vec != nullptr && !ortho;     // no box: the orthorhombic path with a zero box table
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CGB_FUSED(M_, S_)                                                                                \
+#define CGB_FUSED_MODE(M_, S_, MODE_)                                                                     \
     do {                                                                                                 \
-        auto kern = measure_fused_kernel<M_, S_>;                                                        \
+        auto kern = measure_fused_kernel<M_, S_, MODE_>;                                                 \
         CGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, kConsumers + 32, smem, st>>>(q);                                                    \
         return (int)cudaGetLastError();                                                                  \
     } while (0)
+#define CGB_FUSED(M_, S_)                         \
+    do {                                          \
+        if (mode == 3) CGB_FUSED_MODE(M_, S_, 3); \
+        if (mode == 2) CGB_FUSED_MODE(M_, S_, 2); \
+        if (mode == 1) CGB_FUSED_MODE(M_, S_, 1); \
+        CGB_FUSED_MODE(M_, S_, 0);                \
+    } while (0)
+    const int mode = (values ? 1 : 0) | (hist ? 2 : 0);
     if (triclinic && shape == CGB_SHAPE_EAD) CGB_FUSED(MIC_TRICLINIC, CGB_SHAPE_EAD);
     if (triclinic) CGB_FUSED(MIC_TRICLINIC, CGB_SHAPE_EEAA);
     if (shape == CGB_SHAPE_EAD) CGB_FUSED(MIC_ORTHO, CGB_SHAPE_EAD);
     CGB_FUSED(MIC_ORTHO, CGB_SHAPE_EEAA);
+#undef CGB_FUSED_MODE
 #undef CGB_FUSED
 }
 
@@ -541,10 +551,10 @@ extern "C" int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t wa
     const int64_t budget = 112 * 1024;
     const int64_t per_slot = 22 + (with_hist ? 4 * (int64_t)n_bins : 0);
     // everything that does not depend on the plan: barriers, lists, reduction scratch, NaN counters, 7 x 4 KB records
-    const int64_t fixed = 128 + 2 * (1 + cgb::kRoles) + 16 + cgb::kRoles * 4 + 128 +
+    const int64_t fixed = 192 + 2 * (1 + cgb::kRoles) + 16 + cgb::kRoles * 4 + 128 + cgb::kWarps * cgb::kRoleTableBytes +
                           (int64_t)cgb::kWarps * 2 * CGB_MEAS_EDGE_CHUNKS * 32 * 32 + 64;
     auto stages_for = [](int64_t span) { return 2 * (4 * (12 * span + 48 + 16 + 12) + 64 + 128 + 128); };
-    const int64_t min_span = 64, best_span = 384;
+    const int64_t min_span = 64, best_span = 544;
     int64_t slots = std::min<int64_t>(want_slots, (budget - fixed - stages_for(min_span)) / per_slot);
     slots = std::max<int64_t>(slots, 1);
     int64_t span = best_span;

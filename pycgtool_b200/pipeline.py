@@ -92,8 +92,19 @@ def _compile(mapping, bondset, map_plan):
     if not (np.array_equal(bead0[match], bond_plan.tiles["bead0"]) and
             (nbeads[match] >= bond_plan.tiles["span"]).all() and len(np.unique(match)) == len(match)):
         return None
-    fp.meas_of_tile = np.full(fp.n_tiles, -1, dtype=np.int32)
-    fp.meas_of_tile[match] = np.arange(len(match), dtype=np.int32)
+    meas_of_tile = np.full(fp.n_tiles, -1, dtype=np.int32)
+    meas_of_tile[match] = np.arange(len(match), dtype=np.int32)
+    # launch order: tiles with bonded terms (instruction-bound) spread evenly among the others (HBM-bound), so that an
+    # SM holds one of each at a time and the term arithmetic hides behind the streaming of the solvent
+    with_terms = np.nonzero(meas_of_tile >= 0)[0]
+    without = np.nonzero(meas_of_tile < 0)[0]
+    if len(with_terms) and len(without):
+        pos_a = (np.arange(len(with_terms)) + 0.5) / len(with_terms)
+        pos_b = (np.arange(len(without)) + 0.5) / len(without)
+        order = np.concatenate([with_terms, without])[np.argsort(np.concatenate([pos_a, pos_b]), kind="stable")]
+        fp.tiles = np.ascontiguousarray(t[order]).reshape(-1)
+        meas_of_tile = meas_of_tile[order]
+    fp.meas_of_tile = np.ascontiguousarray(meas_of_tile)
     return fp
 
 

@@ -226,7 +226,7 @@ def test_measure_plan_covers_every_column(options, system, dihedrals, tmp_path):
     bondset = BondSet(bnd_path, options)
     plan = bondset.compile_plan(cg_top)
     check_measure_plan(plan)
-    assert (plan.tiles["ngroups"] <= _lib.MEAS_WARPS).all() and (plan.tiles["span"] <= 384).all()
+    assert (plan.tiles["ngroups"] <= _lib.MEAS_WARPS).all() and (plan.tiles["span"] <= 544).all()
     assert plan.shape == (_lib.SHAPE_EAD if plan.counts[2] else _lib.SHAPE_EEAA)
     per_molecule = max(len(bonds) for bonds in bondset._molecules.values())
     assert plan.max_slots <= max(per_molecule, 8)

@@ -412,7 +412,7 @@ def measure_leg(dev, peak_gbs, workload="s3", with_cpu=True, with_e2e=True):
     return leg
 
 
-def pipeline_leg(dev, peak_gbs, frames=64):
+def pipeline_leg(dev, peak_gbs, frames=64, workload="membrane"):
     """mapping + measurement in ONE kernel (cgb_map_measure) on a quarter-size S5 membrane, against the
     two separate launches (K1 then K2) on the same inputs.  Bytes: 12 N + 12 B + 4 M + 48 per frame."""
     import numpy as np
@@ -420,13 +420,13 @@ def pipeline_leg(dev, peak_gbs, frames=64):
     from pycgtool_b200 import BondSet, Frame, Mapping, map_and_measure, pipeline
     from workloads import synth
     from workloads.synth import Options
-    sysm = synth.s5(scale=0.25)
+    sysm = synth.s5(scale=0.25) if workload == "membrane" else synth.small_molecule()
     map_path, bnd_path = sysm.write_files()
-    xyz = sysm.coordinates_device(frames, dev, chunk=8)
+    xyz = sysm.coordinates_device(frames, dev, chunk=8 if workload == "membrane" else 1 << 16)
     box = sysm.box_vectors(frames)
     mapper, bonds, bonds2 = Mapping(map_path, Options()), BondSet(bnd_path, Options()), BondSet(bnd_path, Options())
     frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
-    cg = map_and_measure(mapper, bonds, frame)
+    cg = map_and_measure(mapper, bonds, frame, fused=True)
     map_plan = mapper._plan_for(frame._topology)
     fused = pipeline._fused_plan(mapper, bonds, map_plan) is not None
     st = bonds._state
@@ -467,7 +467,8 @@ def pipeline_leg(dev, peak_gbs, frames=64):
     ms = ms_fused if fused else ms_sep
     return {"what": "Mapping.apply + BondSet.apply as one pass over the atoms (map_and_measure): beads written once, "
                     "never re-read; values + statistics + histograms in the same kernel",
-            "workload": f"quarter-size S5 membrane: {n_atoms:,} atoms -> {n_beads:,} beads, {n_terms:,} terms, {frames} frames",
+            "workload": f"{'quarter-size S5 membrane' if workload == 'membrane' else 'S3 small molecule'}: {n_atoms:,} atoms -> "
+                        f"{n_beads:,} beads, {n_terms:,} terms, {frames} frames",
             "fused_kernel": fused, "ms_per_step": ms, "separate_k1_k2_ms": ms_sep,
             "atom_frames_per_s": frames * n_atoms / (ms * 1e-3), "bond_measures_per_s": frames * n_terms / (ms * 1e-3),
             "algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9,
@@ -478,7 +479,7 @@ def pipeline_leg(dev, peak_gbs, frames=64):
 def north_star_leg(dev, peak_gbs, world, rank, td, mode, scale=1.0):
     """BASELINE.json configs[4]: S5 (20 M atoms), full map + bond statistics, frames sharded over the ranks, the
     per-Bond moments and histograms combined by ONE NCCL all-reduce of the packed buffer (cgb_allreduce_partials).
-    A step = map_and_measure (fused K1+K2) -> all-reduce -> Boltzmann epilogue -> fitted parameters on the host:
+    A step = map_and_measure (K1 + K2) -> all-reduce -> Boltzmann epilogue -> fitted parameters on the host:
     everything, the collective included, inside the timed region.  mode 'strong': 512 frames in total;
     'weak': 256 frames per GPU."""
     import numpy as np
@@ -545,10 +546,11 @@ def north_star_leg(dev, peak_gbs, world, rank, td, mode, scale=1.0):
     coll_us = 1e3 * start.elapsed_time(stop) / 20
     plan = st.plan
     n_terms, n_atoms = plan.n_cols, sysm.n_atoms
-    bytes_alg = frames * (12 * n_atoms + 12 * plan.n_beads + 48)
+    touched = len(np.unique(plan.col_beads))
+    bytes_alg = frames * (12 * n_atoms + 12 * plan.n_beads + 12 * touched + 48)   # K1 + the beads K2 reads back
     return {"workload": f"S5 x{scale:g}: {n_atoms:,} atoms -> {plan.n_beads:,} beads, {n_terms:,} terms per frame, "
                         f"{plan.n_bonds} Bonds; {total} frames over {world} GPU(s) ({frames} on this rank)",
-            "scaling": mode, "step": "map_and_measure (fused K1+K2, stats-only) -> NCCL all-reduce of "
+            "scaling": mode, "step": "map_and_measure (K1 then K2 on the resident beads, stats-only) -> NCCL all-reduce of "
                                      "[moments | histograms] -> Boltzmann epilogue -> parameters on the host",
             "ms_per_step": ms, "atom_frames_per_s": total * n_atoms / (ms * 1e-3),
             "bond_measures_per_s": total * n_terms / (ms * 1e-3), "kernel_ms": kernel_ms,
@@ -806,6 +808,7 @@ def run_b200(args):
         if "pipeline" in legs:
             torch.cuda.empty_cache()
             line["pipeline"] = guarded("pipeline", lambda: pipeline_leg(dev, peak_gbs))
+            line["pipeline_s3"] = guarded("pipeline_s3", lambda: pipeline_leg(dev, peak_gbs, 1 << 18, "s3"))
         if "ingest" in legs and args.workload == "s2":
             torch.cuda.empty_cache()
             line["ingest"] = guarded("ingest", lambda: ingest_leg(sysm, mapper, plan, dev))

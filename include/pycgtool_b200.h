@@ -395,10 +395,14 @@ int cgb_xtc_scan(const uint8_t* data, int64_t n_bytes, int64_t max_frames, CgbXt
  * sequential walk per frame that records a checkpoint every 16 coordinate groups, then one thread per
  * checkpoint decodes in parallel.  workspace: device scratch of cgb_xtc_workspace_bytes(), 16-byte aligned. */
 int64_t cgb_xtc_workspace_bytes(int64_t n_frames, int64_t n_atoms);
+/* The decoder does not trust the bit stream: a frame whose stream leaves the small-difference table or runs past
+ * its payload (truncated / corrupt file) is not decoded and counted in *bad_frames (device int32, accumulated;
+ * may be NULL); no byte outside the frame's payload is read and none outside its rows of xyz written. */
 int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtcFrame* frames, int64_t n_frames,
-                   int64_t n_atoms, float* xyz, void* workspace, int64_t workspace_bytes, void* stream);
+                   int64_t n_atoms, float* xyz, void* workspace, int64_t workspace_bytes, int32_t* bad_frames,
+                   void* stream);
 
-/* Host: the same decoder on the CPU (all pointers host memory). */
+/* Host: the same decoder on the CPU (all pointers host memory).  CGB_EINVAL when a frame's stream is invalid. */
 int cgb_xtc_decode_host(const uint8_t* data, const CgbXtcFrame* frames, int64_t n_frames, int64_t n_atoms,
                         float* xyz);
 

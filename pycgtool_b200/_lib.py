@@ -131,7 +131,7 @@ SIGNATURES = {
     "cgb_comm_broadcast": (_int, [_vp, _vp, _i64, _i32, _vp]),
     "cgb_xtc_scan": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cgb_xtc_workspace_bytes": (_i64, [_i64, _i64]),
-    "cgb_xtc_decode": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "cgb_xtc_decode": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "cgb_xtc_decode_host": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "cgb_xtc_encode": (_int, [_vp, _vp, _vp, _i64, _i64, ctypes.c_float, _vp, _i64, _vp]),
 }

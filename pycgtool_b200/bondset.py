@@ -44,10 +44,27 @@ class Bond:
         self.gromacs_type_id = func_form.gromacs_type_id_by_natoms(len(atoms))
         self._values = []
         self._source = None      # (BondSet state, bond id) when measured on the GPU
-        self.histogram = None    # (counts uint64 (nbins,), edges float64 (nbins+1,)) after boltzmann_invert
+        self._histogram = None   # (counts, lo, hi) after boltzmann_invert; the edges are made on demand
 
     def __iter__(self):
         return iter(self.atoms)
+
+    @property
+    def histogram(self):
+        """``(counts uint64 (nbins,), edges float64 (nbins + 1,))`` of the measured values after
+        ``boltzmann_invert`` (``numpy.histogram`` semantics), or None."""
+        if self._histogram is None:
+            return None
+        counts, lo, hi = self._histogram
+        return counts, np.linspace(lo, hi, len(counts) + 1)
+
+    @histogram.setter
+    def histogram(self, value):
+        if value is None:
+            self._histogram = None
+        else:
+            counts, edges = value
+            self._histogram = (counts, float(edges[0]), float(edges[-1]))
 
     # ---- values: frame-major float32, fetched from the GPU on first use (bondset.py:531)
     @property
@@ -244,9 +261,15 @@ class _MeasureState:
             self.reduced = True
         out = torch.empty((plan.n_bonds, _lib.NOUT), dtype=torch.float64, device=self.dev)
         self._boltzmann(temp, 0, out)
-        host = torch.cat([out.reshape(-1), self.partials[:, 6]]).cpu().numpy()
-        result = host[:plan.n_bonds * _lib.NOUT].reshape(plan.n_bonds, _lib.NOUT)
-        self.counts_host = host[plan.n_bonds * _lib.NOUT:].astype(np.int64)
+        # one device-to-host copy: fitted parameters, value counts and (first time) the histograms
+        want_hist = self.hist is not None and self.hist_host is None
+        parts = [out.reshape(-1), self.partials[:, 6]] + ([self.hist.reshape(-1)] if want_hist else [])
+        host = torch.cat(parts).cpu().numpy()
+        n_out = plan.n_bonds * _lib.NOUT
+        result = host[:n_out].reshape(plan.n_bonds, _lib.NOUT)
+        self.counts_host = host[n_out:n_out + plan.n_bonds].astype(np.int64)
+        if want_hist:
+            self.hist_host = np.rint(host[n_out + plan.n_bonds:]).astype(np.uint64).reshape(self.hist.shape)
         flagged = np.nonzero(result[:, 4] == 1.0)[0]
         if len(flagged):
             n_cols = plan.n_cols
@@ -290,9 +313,8 @@ class _MeasureState:
             return          # nothing finite was measured: leave eqm / fconst as None
         _finish_bond(bond, mean, var, temp, device_result=(eqm, fconst))
         if self.hist_host is not None:
-            edges = np.linspace(float(self.hist_lo_host[bond_id]), float(self.hist_hi_host[bond_id]),
-                                self.hist_host.shape[1] + 1)
-            bond.histogram = (self.hist_host[bond_id].copy(), edges)
+            bond._histogram = (self.hist_host[bond_id], float(self.hist_lo_host[bond_id]),
+                               float(self.hist_hi_host[bond_id]))
 
 
 class BondSet:
@@ -692,6 +714,14 @@ class BondSet:
                 device.dptr(shift), device.dptr(wide_values), n_cols, device.dptr(partials), device.dptr(hist),
                 device.dptr(hist_lo), device.dptr(hist_hi), int(nbins), stream), "cgb_measure")
 
+    def _release(self):
+        """Drop the device buffers of the previous measurement (state, and the Bonds' references to it)."""
+        self._state = None
+        for bond in itertools.chain(*self._molecules.values()):
+            if bond._source is not None:
+                bond._source = None
+                bond._values = []
+
     # ------------------------------------------------------------------ apply (bondset.py:496-531)
     def apply(self, frame, histogram=True, store_values=True):
         """Measure every bonded term in every frame of ``frame`` on the GPU.
@@ -705,7 +735,7 @@ class BondSet:
         import torch
         device.require_cuda()
         lib = _lib.load()
-        self._state = None          # release the previous call's buffers before allocating new ones
+        self._release()             # the previous call's buffers go before new ones are allocated
         plan = self._plan_for(frame._topology)
         traj = frame._trajectory
         xyz = traj.device_xyz()
@@ -719,8 +749,8 @@ class BondSet:
         # mdtraj: orthorhombic fast path only if every angle of every frame is ~90 degrees; with the frames
         # sharded across GPUs both decisions are taken over the whole trajectory, like the reference's
         box_dev = traj.device_box_vectors(dev)
-        has_box = dist.all_true(box_dev is not None, device=dev)
-        ortho = int(dist.all_true(bool(traj.orthorhombic), device=dev))
+        _, has_box, ortho = traj.global_box_flags(dev)
+        ortho = int(ortho)
         if not has_box:
             box_dev = None
         source = (xyz, box_dev, ortho)

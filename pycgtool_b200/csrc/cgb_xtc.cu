@@ -60,18 +60,20 @@ __host__ __device__ inline uint32_t load_be32(const uint8_t* p) {
 // refills 32 bits at a time and can start at any bit position.
 struct BitReader {
     const uint8_t* base;
-    uint64_t word;  // index of the next 32-bit word to load
-    uint64_t buf;   // low `have` bits are valid
+    uint64_t word;    // index of the next 32-bit word to load
+    uint64_t buf;     // low `have` bits are valid
+    uint64_t nwords;  // words of the payload: reads beyond it return zeros (a corrupt stream cannot leave the frame)
     int have;
     __host__ __device__ inline uint32_t load_word(uint64_t w) const {
+        if (w >= nwords) return 0u;
 #ifdef __CUDA_ARCH__
         return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(base) + w), 0, 0x0123);
 #else
         return load_be32(base + 4 * w);
 #endif
     }
-    __host__ __device__ explicit BitReader(const uint8_t* data, uint64_t bitpos = 0)
-        : base(data), word(bitpos >> 5), buf(0), have(0) {
+    __host__ __device__ BitReader(const uint8_t* data, uint64_t payload_bytes, uint64_t bitpos = 0)
+        : base(data), word(bitpos >> 5), buf(0), nwords((payload_bytes + 3) >> 2), have(0) {
         const int skip = (int)(bitpos & 31);
         if (skip) {
             buf = load_word(word++) & (0xffffffffu >> skip);
@@ -188,7 +190,9 @@ struct GroupState {
     int run;       // current run length (persists while the flag bit is 0)
 };
 
-// Decode up to `max_groups` groups starting at the reader's position; returns the groups decoded.
+// Decode up to `max_groups` groups starting at the reader's position; returns the groups decoded, or -1 when the
+// stream is not a valid one: the small-difference table entry leaves [kFirstIdx, kLastIdx] or the reader passes the
+// end of the payload (truncated or corrupt file).  Nothing is read or written outside the frame in either case.
 __host__ __device__ inline int decode_groups(BitReader& r, const CgbXtcFrame& fr, const FrameCoding& c,
                                              GroupState& st, int max_groups, float* xyz) {
     const int natoms = fr.natoms;
@@ -239,6 +243,7 @@ __host__ __device__ inline int decode_groups(BitReader& r, const CgbXtcFrame& fr
             ++i;
         }
         smallidx += is_smaller;
+        if (smallidx < kFirstIdx || smallidx > kLastIdx || r.position() > r.nwords * 32) return -1;
         if (is_smaller < 0) {
             smallnum = smaller;
             smaller = smallidx > kFirstIdx ? CGB_MAGIC(smallidx - 1) / 2 : 0;
@@ -255,12 +260,12 @@ __host__ __device__ inline int decode_groups(BitReader& r, const CgbXtcFrame& fr
     return groups;
 }
 
-// Decode one frame's compressed coordinates into xyz[natoms][3] (sequential; host path).
-__host__ __device__ inline void decode_frame(const uint8_t* payload, const CgbXtcFrame& fr, float* xyz) {
+// Decode one frame's compressed coordinates into xyz[natoms][3] (sequential; host path).  False: invalid stream.
+__host__ __device__ inline bool decode_frame(const uint8_t* payload, const CgbXtcFrame& fr, float* xyz) {
     const FrameCoding c = frame_coding(fr);
-    BitReader r(payload);
+    BitReader r(payload, (uint64_t)fr.nbytes);
     GroupState st = {0, fr.smallidx, 0};
-    decode_groups(r, fr, c, st, 0x7fffffff, xyz);
+    return decode_groups(r, fr, c, st, 0x7fffffff, xyz) >= 0 && st.atom >= fr.natoms;
 }
 
 __host__ __device__ inline void decode_raw(const uint8_t* payload, int natoms, float* xyz) {
@@ -315,7 +320,7 @@ __device__ __forceinline__ uint32_t ring_peek6(const uint32_t* ring, uint32_t po
 __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict__ data, int64_t n_bytes,
                                                       const CgbXtcFrame* __restrict__ frames, int64_t n_frames,
                                                       int64_t n_atoms, XtcCheckpoint* __restrict__ checks,
-                                                      int32_t* __restrict__ n_checks) {
+                                                      int32_t* __restrict__ n_checks, int32_t* __restrict__ bad_frames) {
     __shared__ uint32_t ring[2 * kWalkHalfWords];
     const int64_t f = blockIdx.x;
     const int lane = threadIdx.x;
@@ -327,8 +332,10 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
     }
     const FrameCoding c = frame_coding(fr);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(data + fr.offset);
-    // words of the image readable from the payload start (the image is padded by 8 bytes)
-    const int64_t avail = (n_bytes + 8 - fr.offset) >> 2;
+    // words of the image readable from the payload start (the image is padded by 8 bytes), and of the payload
+    const int64_t avail = min((n_bytes + 8 - fr.offset) >> 2, ((int64_t)fr.nbytes + 3) >> 2);
+    const uint32_t end_bits = (uint32_t)((((int64_t)fr.nbytes + 3) >> 2) * 32);
+    bool bad = false;   // lane 0: the stream is not a valid one (see decode_groups)
 
     auto load_half = [&](int h) {
         uint32_t* dst = ring + (h & 1) * kWalkHalfWords;
@@ -371,6 +378,10 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
                     pos += fullbits + 6u + (uint32_t)smalls * (uint32_t)smallidx;
                     atom += smalls + 1;
                     smallidx += is_smaller - 1;
+                    if (smallidx < kFirstIdx || smallidx > kLastIdx) {
+                        bad = true;
+                        break;
+                    }
                     v = ring_peek6(ring, pos + fullbits);
                 } else {
                     atom += run / 3 + 1;
@@ -378,8 +389,12 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
                     v = v0;
                 }
                 ++group;
+                if (pos > end_bits) {
+                    bad = true;
+                    break;
+                }
             }
-            done = atom >= fr.natoms;
+            done = bad || atom >= fr.natoms;
         }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done) break;
@@ -389,14 +404,17 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
         load_half(hl);
         __syncwarp();
     }
-    if (lane == 0) n_checks[f] = nc;
+    if (lane == 0) {
+        n_checks[f] = bad ? -1 : nc;      // a bad frame is not decoded
+        if (bad && bad_frames) atomicAdd(bad_frames, 1);
+    }
 }
 
 __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restrict__ data,
                                                          const CgbXtcFrame* __restrict__ frames, int64_t n_frames,
                                                          int64_t n_atoms, const XtcCheckpoint* __restrict__ checks,
                                                          const int32_t* __restrict__ n_checks,
-                                                         float* __restrict__ xyz) {
+                                                         float* __restrict__ xyz, int32_t* __restrict__ bad_frames) {
     const int64_t f = blockIdx.y;
     const int64_t cpf = checks_per_frame(n_atoms);
     const CgbXtcFrame fr = frames[f];
@@ -405,13 +423,13 @@ __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restri
         if (blockIdx.x == 0 && threadIdx.x == 0) decode_raw(data + fr.offset, fr.natoms, out);
         return;
     }
-    const int nc = n_checks[f];
+    const int nc = n_checks[f];     // -1: the walk found the stream invalid, the frame stays undecoded
     const FrameCoding c = frame_coding(fr);
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nc; k += (int64_t)gridDim.x * blockDim.x) {
         const XtcCheckpoint cp = checks[f * cpf + k];
-        BitReader r(data + fr.offset, cp.bitpos);
+        BitReader r(data + fr.offset, (uint64_t)fr.nbytes, cp.bitpos);
         GroupState st = {(int)cp.atom, (int)(cp.state & 0xff), (int)(cp.state >> 8)};
-        decode_groups(r, fr, c, st, kCheckEvery, out);
+        if (decode_groups(r, fr, c, st, kCheckEvery, out) < 0 && bad_frames) atomicAdd(bad_frames, 1);
     }
 }
 
@@ -543,6 +561,12 @@ extern "C" int cgb_xtc_scan(const uint8_t* data, int64_t n_bytes, int64_t max_fr
             fr.nbytes = (int32_t)load_be32(data + pos + 88);
             fr.offset = pos + 92;
             if (fr.smallidx < kFirstIdx || fr.smallidx > kLastIdx || fr.nbytes < 0) return CGB_EINVAL;
+            if (!(fr.precision > 0.0f) || !std::isfinite(fr.precision)) return CGB_EINVAL;
+            for (int d = 0; d < 3; ++d) {
+                // sizeint = maxint - minint + 1 must be a positive 32-bit count (it is a divisor in the decoder)
+                const int64_t size = (int64_t)fr.maxint[d] - (int64_t)fr.minint[d] + 1;
+                if (size < 1 || size > 0xffffffffLL) return CGB_EINVAL;
+            }
             if ((int64_t)fr.nbytes * 8 >= ((int64_t)1 << 32)) return CGB_ERANGE;  // 32-bit bit positions
             next = pos + 92 + (((int64_t)fr.nbytes + 3) / 4) * 4;
         }
@@ -600,15 +624,23 @@ extern "C" int cgb_xtc_decode_host(const uint8_t* data, const CgbXtcFrame* frame
     if (!data || !frames || !xyz) return CGB_EINVAL;
     for (int64_t f = 0; f < n_frames; ++f)
         if (frames[f].natoms != n_atoms) return CGB_EINVAL;
+    for (int64_t f = 0; f < n_frames; ++f) {   // a table not made by cgb_xtc_scan: the same checks again
+        const CgbXtcFrame& fr = frames[f];
+        if (fr.natoms <= 9) continue;
+        if (fr.smallidx < kFirstIdx || fr.smallidx > kLastIdx || fr.nbytes < 0 || !(fr.precision > 0.0f)) return CGB_EINVAL;
+        for (int d = 0; d < 3; ++d)
+            if ((int64_t)fr.maxint[d] - (int64_t)fr.minint[d] + 1 < 1) return CGB_EINVAL;
+    }
     // frames are independent: decode them on all host cores
+    std::atomic<int64_t> bad(0);
     parallel_frames(n_frames, [&](int64_t f) {
         float* out = xyz + (size_t)f * n_atoms * 3;
         if (frames[f].natoms <= 9)
             decode_raw(data + frames[f].offset, frames[f].natoms, out);
-        else
-            decode_frame(data + frames[f].offset, frames[f], out);
+        else if (!decode_frame(data + frames[f].offset, frames[f], out))
+            bad.fetch_add(1);
     });
-    return CGB_OK;
+    return bad.load() ? CGB_EINVAL : CGB_OK;   // truncated or corrupt coordinate stream
 }
 
 extern "C" int64_t cgb_xtc_workspace_bytes(int64_t n_frames, int64_t n_atoms) {
@@ -618,7 +650,7 @@ extern "C" int64_t cgb_xtc_workspace_bytes(int64_t n_frames, int64_t n_atoms) {
 
 extern "C" int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtcFrame* frames, int64_t n_frames,
                               int64_t n_atoms, float* xyz, void* workspace, int64_t workspace_bytes,
-                              void* stream) {
+                              int32_t* bad_frames, void* stream) {
     using namespace cgb;
     if (n_frames < 0 || n_atoms < 0 || n_bytes < 0) return CGB_EINVAL;
     if (n_frames == 0 || n_atoms == 0) return CGB_OK;
@@ -630,12 +662,12 @@ extern "C" int cgb_xtc_decode(const uint8_t* data, int64_t n_bytes, const CgbXtc
     XtcCheckpoint* checks = static_cast<XtcCheckpoint*>(workspace);
     int32_t* n_checks = reinterpret_cast<int32_t*>(checks + n_frames * checks_per_frame(n_atoms));
     xtc_walk_kernel<<<(unsigned)n_frames, 32, 0, st>>>(data, n_bytes, frames, n_frames, n_atoms, checks,
-                                                                    n_checks);
+                                                                    n_checks, bad_frames);
     CGB_CUDA_TRY(cudaGetLastError());
     const int64_t max_checks = checks_per_frame(n_atoms);
     const unsigned bx = (unsigned)std::min<int64_t>((max_checks + 127) / 128, 1024);
     dim3 grid(bx, (unsigned)n_frames);
-    xtc_decode_kernel<<<grid, 128, 0, st>>>(data, frames, n_frames, n_atoms, checks, n_checks, xyz);
+    xtc_decode_kernel<<<grid, 128, 0, st>>>(data, frames, n_frames, n_atoms, checks, n_checks, xyz, bad_frames);
     return (int)cudaGetLastError();
 }
 

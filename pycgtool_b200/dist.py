@@ -135,6 +135,16 @@ def all_true(flag, device=None):
     return bool(t.item())
 
 
+def all_true_many(flags, device=None):
+    """Element-wise logical AND of a list of Python bools over all ranks, in ONE collective."""
+    flags = tuple(bool(f) for f in flags)
+    if not is_distributed():
+        return flags
+    t = torch.tensor([1 if f else 0 for f in flags], dtype=torch.int32, device=device)
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    return tuple(bool(v) for v in t.tolist())
+
+
 def merge_partials(shards):
     """Sum a list of per-shard partial tensors (what the all-reduce computes); used by tests
     and by single-process multi-shard runs."""

@@ -160,8 +160,10 @@ def read_xtc(path, topology=None):
     _check_topology(topology, n_atoms)
     xyz = np.empty((nf, n_atoms, 3), dtype=np.float32)
     padded = np.concatenate([image, np.zeros(8, dtype=np.uint8)])
-    _lib.check(_lib.load().cgb_xtc_decode_host(_lib.ptr(padded), _lib.ptr(table), nf, n_atoms, _lib.ptr(xyz)),
-               "cgb_xtc_decode_host")
+    rc = _lib.load().cgb_xtc_decode_host(_lib.ptr(padded), _lib.ptr(table), nf, n_atoms, _lib.ptr(xyz))
+    if rc == -1:
+        raise OSError(f"'{path}': truncated or corrupt XTC coordinate stream")
+    _lib.check(rc, "cgb_xtc_decode_host")
     return Trajectory(xyz, topology, time, box if box.any() else None)
 
 
@@ -193,13 +195,16 @@ def read_xtc_device(path, topology=None, device=None):
         raise OSError(f"'{path}': XTC format is not supported ({exc})") from exc
     _check_topology(topology, n_atoms)
     xyz = torch.empty((nf, n_atoms, 3), dtype=torch.float32, device=device)
-    decode_image_device(pinned, size, table, nf, n_atoms, xyz)
+    bad = torch.zeros(1, dtype=torch.int32, device=device)
+    decode_image_device(pinned, size, table, nf, n_atoms, xyz, bad_frames=bad)
     torch.cuda.current_stream().synchronize()      # the staging buffers may be released now
+    if int(bad.item()):
+        raise OSError(f"'{path}': {int(bad.item())} frame(s) hold a truncated or corrupt coordinate stream")
     return Trajectory(None, topology, time, box if box.any() else None, xyz_device=xyz)
 
 
 def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, block_bytes=128 << 20, on_block=None,
-                        image_dev=None, n_streams=4):
+                        image_dev=None, n_streams=4, bad_frames=None):
     """Upload an XTC file image from pinned host memory and decode it on the GPU, pipelined: the image goes
     up in blocks of whole frames (~``block_bytes`` each) on a copy stream, and each block is decoded on one of
     ``n_streams`` side streams as soon as it has arrived.  A block's decode starts with a sequential walk per
@@ -244,13 +249,13 @@ def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, bloc
                 worker.wait_event(entry)
             worker.wait_event(ready)
             decode_device(image_dev, n_bytes, table_dev, f1 - f0, n_atoms, xyz_dev[f0:], frame0=f0,
-                          workspace_key=k % len(workers))
+                          workspace_key=k % len(workers), bad_frames=bad_frames)
             if on_block is not None:
                 on_block(f0, f1)
         b0 = b1
     for worker in workers:
         main.wait_stream(worker)
-    for t in (image_dev, table_dev, xyz_dev):
+    for t in (image_dev, table_dev, xyz_dev) + ((bad_frames,) if bad_frames is not None else ()):
         for st in workers + [copy]:
             t.record_stream(st)
     return image_dev
@@ -267,10 +272,12 @@ def _side_stream(device, name):
     return _SIDE_STREAMS[key]
 
 
-def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, block=4096, frame0=0, workspace_key=None):
+def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, block=4096, frame0=0, workspace_key=None,
+                  bad_frames=None):
     """``cgb_xtc_decode`` over blocks of frames (one launch handles at most 65535 frames; the
     checkpoint workspace is sized for one block and reused).  Decodes frames [frame0, frame0 + n_frames)
-    of the table into ``xyz_dev[0:n_frames]``."""
+    of the table into ``xyz_dev[0:n_frames]``.  ``bad_frames``: device int32 counter of frames whose bit stream
+    is invalid (truncated or corrupt file); the caller reads it once the stream has finished."""
     from . import device as dev
     lib = _lib.load()
     block = int(min(block, max(n_frames, 1)))
@@ -281,7 +288,7 @@ def decode_device(image_dev, n_bytes, table_dev, n_frames, n_atoms, xyz_dev, blo
         f1 = min(n_frames, f0 + block)
         _lib.check(lib.cgb_xtc_decode(dev.dptr(image_dev), n_bytes, dev.dptr(table_dev[(frame0 + f0) * frame_bytes:]),
                                       f1 - f0, n_atoms, dev.dptr(xyz_dev[f0:]), dev.dptr(workspace), ws_bytes,
-                                      dev.stream_handle()), "cgb_xtc_decode")
+                                      dev.dptr(bad_frames), dev.stream_handle()), "cgb_xtc_decode")
 
 
 _WORKSPACES = {}

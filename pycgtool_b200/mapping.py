@@ -586,7 +586,7 @@ class Mapping:
         # mapping.py:406-408: lengths only, and no PBC at all if any length of any frame is zero
         box = frame.unitcell_lengths
         # evaluated over the whole trajectory, i.e. over every frame shard when sharded across GPUs
-        if not dist.all_true(box is not None and bool(np.all(box)), device=device.default_device()):
+        if not traj.global_box_flags(device.default_device())[0]:
             box = None
         host_xyz = None
         if not traj.on_device and traj.xyz.nbytes >= STREAM_THRESHOLD_BYTES and plan.n_beads:
@@ -596,6 +596,7 @@ class Mapping:
             out = self.map_device(plan, traj.device_xyz(), box)
         new = Frame.from_arrays(plan.cg_topology if cg_frame is None else cg_frame._topology, xyz=host_xyz,
                                 unitcell_vectors=traj.unitcell_vectors, time=frame.time, xyz_device=out)
+        new._trajectory._global_flags = traj._global_flags      # same unit cell: the decisions carry over
         if cg_frame is not None and hasattr(cg_frame, "_trajectory"):
             cg_frame._trajectory += new._trajectory
             cg_frame._attach(cg_frame._trajectory)

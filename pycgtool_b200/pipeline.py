@@ -130,12 +130,15 @@ def _device_fused(fp, dev):
     return fp._dev[key]
 
 
-def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, fused=True):
+def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, fused=None):
     """``cg = mapping.apply(frame); bondset.apply(cg)`` in one pass over the atoms; returns ``cg``.
 
     Afterwards ``bondset.boltzmann_invert()`` and every ``bond.values`` behave exactly as after the two
-    separate calls.  ``fused=False`` (or a system the fused kernel does not support, or a host trajectory
-    large enough to be streamed) runs the two stages one after the other.
+    separate calls.  ``fused=True`` asks for the single fused kernel (``cgb_map_measure``); the default runs the two
+    kernels back to back on the device-resident trajectory, which is the faster of the two on B200: stage 2 is bound
+    by instruction issue, not by HBM, so re-reading the beads costs less than sharing an SM's warps between mapping
+    and measurement (measured in ``bench.py``'s ``pipeline`` leg).  A system the fused kernel does
+    not support, or a host trajectory large enough to be streamed, always takes the two stages.
     """
     import torch
     device.require_cuda()
@@ -143,11 +146,28 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     map_plan = mapping._plan_for(frame._topology)
     traj = frame._trajectory
     fp = _fused_plan(mapping, bondset, map_plan) if fused else None
+    bondset._release()                  # the previous pass's CG trajectory and values go before new ones are allocated
     from . import mapping as _mapping_module
     streamed = (not traj.on_device) and traj.xyz.nbytes >= _mapping_module.STREAM_THRESHOLD_BYTES
     if fp is None or streamed:
         cg = mapping.apply(frame)
         bondset.apply(cg, histogram=histogram, store_values=store_values)
+        state = bondset._state
+        if not streamed and state is not None and state.n_frames:
+            xyz_in, cg_out = traj.device_xyz(), cg._trajectory.device_xyz()
+            box = frame.unitcell_lengths
+            if not traj.global_box_flags(xyz_in.device)[0]:
+                box = None
+            box_len_dev = None if box is None else device.to_device(box, xyz_in.device, dtype=np.float32)
+            nbins_ = 0 if state.hist is None else int(state.hist.shape[1])
+
+            def relaunch(packed_=state.packed, values_=state.values):
+                """The two launches again (K1 then K2) into the given accumulators; bench.py times this."""
+                mapping.map_device(map_plan, xyz_in, box_len_dev, out=cg_out)
+                bondset._launch_measure(state.plan, state.source, state.n_frames, state.shift, values_, packed_,
+                                        nbins_, state.hist_lo, state.hist_hi)
+
+            state.relaunch = relaunch
         return cg
 
     from .bondset import BondSet, _MeasureState
@@ -158,14 +178,13 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     n_cols = plan.n_cols
     # mapping: box lengths only, and none at all if any length of any frame is zero (mapping.py:406-408)
     box = frame.unitcell_lengths
-    if not dist.all_true(box is not None and bool(np.all(box)), device=dev):
+    lengths_ok, has_vectors, ortho = traj.global_box_flags(dev)
+    if not lengths_ok:
         box = None
     box_len = device.to_device(box, dev, dtype=np.float32) if box is not None else None
     # measurement: full box vectors, orthorhombic fast path as mdtraj decides it (see BondSet.apply)
-    box_vec = traj.device_box_vectors(dev)
-    if not dist.all_true(box_vec is not None, device=dev):
-        box_vec = None
-    ortho = int(dist.all_true(bool(traj.orthorhombic), device=dev))
+    box_vec = traj.device_box_vectors(dev) if has_vectors else None
+    ortho = int(ortho)
 
     d_map = mapping._device_plan(map_plan, dev)         # virtual beads, and K1 for the frame-0 shift
     d_fused = _device_fused(fp, dev)
@@ -216,7 +235,7 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
 
     cg = Frame.from_arrays(map_plan.cg_topology, xyz=None, unitcell_vectors=traj.unitcell_vectors, time=frame.time,
                            xyz_device=out)
-    bondset._state = None
+    cg._trajectory._global_flags = traj._global_flags
     state = _MeasureState(bondset, plan, n_frames, values, packed, nbins, shift, hist_lo, hist_hi, dev,
                           (out, box_vec, ortho))
     state.hist_lo_host, state.hist_hi_host = lo, hi

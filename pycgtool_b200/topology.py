@@ -338,6 +338,21 @@ class Trajectory:
             self._xyz_dev = dev.to_device(self._xyz, device)
         return self._xyz_dev
 
+    def global_box_flags(self, device=None):
+        """``(every box length of every frame is non-zero, a unit cell is present, mdtraj's orthorhombic test)``
+        decided over the WHOLE trajectory: with the frames sharded across GPUs the reference's decisions
+        (``mapping.py:406-408``; mdtraj's ``np.allclose(angles, 90)``) hold for all ranks together, so the three
+        flags are combined in one collective.  Evaluated once per trajectory and handed on to the CG trajectory
+        mapped from it (same unit cell)."""
+        flags = getattr(self, "_global_flags", None)
+        if flags is None:
+            from . import dist
+            lengths = self.unitcell_lengths
+            flags = dist.all_true_many([lengths is not None and bool(np.all(lengths)), self._vectors is not None,
+                                        bool(self.orthorhombic)], device=device)
+            self._global_flags = flags
+        return flags
+
     def drop_device(self):
         """Forget the device copies (the host copy stays): the next use uploads again."""
         if self._xyz is not None:
@@ -376,6 +391,7 @@ class Trajectory:
             self._vectors = None
             self._vectors_dev = None
             self._ortho = None
+            self._global_flags = None
             self.unitcell_lengths = None
             self.unitcell_angles = None
             return
@@ -385,6 +401,7 @@ class Trajectory:
         self._vectors = vectors
         self._vectors_dev = None
         self._ortho = None
+        self._global_flags = None
         self.unitcell_lengths, self.unitcell_angles = lengths_and_angles(vectors)
 
     def slice(self, key):

@@ -620,3 +620,37 @@ def test_statistics_are_reproducible_run_to_run(options):
     for partials, hist in runs[1:]:
         assert np.array_equal(hist, runs[0][1])
         np.testing.assert_allclose(partials, runs[0][0], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("skew", [(0.9, -1.1, 1.3), (1.45, 1.45, 1.45), (2.2, -1.9, 2.6)])
+def test_triclinic_lengths_equal_exhaustive_image_search(options, tmp_path, skew):
+    """Independent check of the triclinic wrap (the reference has no fixture that wraps in a triclinic cell): the
+    kernel's lengths against a float64 exhaustive search over periodic images (tests/bruteforce.py), which shares
+    nothing with mdtraj's reduce-and-search algorithm that both the oracle and the kernel restate."""
+    from pycgtool_b200 import BondSet, Frame
+    from pycgtool_b200.topology import Topology
+    from tests.bruteforce import min_image_distance, skewed_boxes
+    rng = np.random.default_rng(21)
+    n_frames, n_beads = 33, 40
+    names = [f"B{i}" for i in range(n_beads)]
+    top = Topology.from_residue_lists([("MOL", names)])
+    box = skewed_boxes(n_frames, (3.0, 3.1, 2.9), skew, seed=5)
+    frac = rng.uniform(-0.1, 1.1, size=(n_frames, n_beads, 3))
+    xyz = np.einsum("fbi,fij->fbj", frac, box.astype(np.float64)).astype(np.float32)
+    pairs = [(i, (5 * i + 3) % n_beads) for i in range(n_beads) if i != (5 * i + 3) % n_beads]
+    pairs += [(i, i + 1) for i in range(0, n_beads - 1, 2)]
+    pairs = sorted({tuple(sorted(p)) for p in pairs})
+    bnd = tmp_path / "pairs.bnd"
+    bnd.write_text("[ MOL ]\n" + "".join(f"B{a} B{b}\n" for a, b in pairs))
+    options.generate_angles = False
+    bonds = BondSet(bnd, options)
+    bonds.apply(Frame.from_arrays(top, xyz, unitcell_vectors=box))
+    want = min_image_distance(xyz, np.array(pairs), box, reach=4)
+    assert len(bonds["MOL"]) == len(pairs)
+    wrapped = 0
+    for k, bond in enumerate(bonds["MOL"]):
+        got = np.asarray(bond.values, dtype=np.float64)
+        np.testing.assert_allclose(got, want[:, k], rtol=3e-6, atol=3e-6)
+        direct = np.linalg.norm(xyz[:, pairs[k][1]].astype(np.float64) - xyz[:, pairs[k][0]], axis=-1)
+        wrapped += int((want[:, k] < direct - 1e-3).sum())
+    assert wrapped > 0.2 * n_frames * len(pairs)        # the image shift is exercised, not skipped

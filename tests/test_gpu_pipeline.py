@@ -31,7 +31,7 @@ def _both_ways(sysm, n_frames, options, box=True, skew=None, histogram=True, sto
     sep.apply(cg_sep, histogram=histogram, store_values=store_values)
     sep.boltzmann_invert()
     fused = BondSet(bnd_path, options)
-    cg_fused = map_and_measure(mapper, fused, frame, histogram=histogram, store_values=store_values)
+    cg_fused = map_and_measure(mapper, fused, frame, histogram=histogram, store_values=store_values, fused=True)
     assert pipeline._fused_plan(mapper, fused, mapper._plan_for(frame._topology)) is not None, "fused plan not used"
     fused.boltzmann_invert()
     ocg = omap.apply(omap.parse_map(map_path), oracle_system(sysm.topology, xyz, bx))
@@ -111,7 +111,7 @@ def test_sugar_fused(golden, options):
     import json
     frame = Frame(golden / "sugar.gro", golden / "sugar.xtc")
     bonds = BondSet(golden / "sugar.bnd", options)
-    cg = map_and_measure(Mapping(golden / "sugar.map", options), bonds, frame)
+    cg = map_and_measure(Mapping(golden / "sugar.map", options), bonds, frame, fused=True)
     bonds.boltzmann_invert()
     gold, _, _ = fileio.read_xtc(golden / "sugar_out.xtc")
     assert np.array_equal(cg._trajectory.xyz, gold)
@@ -130,7 +130,7 @@ def test_virtual_beads_through_map_and_measure(golden, options, tmp_path):
     measure = BondSet(golden / "martini3" / "naphthalene.bnd", options)
     mapping = Mapping(golden / "martini3" / "naphthalene.map", options)
     frame = Frame(golden / "martini3" / "naphthalene.gro")
-    cg = map_and_measure(mapping, measure, frame)
+    cg = map_and_measure(mapping, measure, frame, fused=True)
     assert np.array_equal(cg._trajectory.xyz, mapping.apply(frame)._trajectory.xyz)
     measure.boltzmann_invert()
     measure.write_itp(tmp_path / "naphthalene_out.itp", mapping)
@@ -148,7 +148,7 @@ def test_unsupported_systems_fall_back_to_two_stages(options):
     mapper = Mapping(map_path, options)
     frame = Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box)
     a, b = BondSet(bnd_path, options), BondSet(bnd_path, options)
-    cg_a = map_and_measure(mapper, a, frame)
+    cg_a = map_and_measure(mapper, a, frame, fused=True)
     assert pipeline._fused_plan(mapper, a, mapper._plan_for(frame._topology)) is None
     cg_b = mapper.apply(frame)
     b.apply(cg_b)

@@ -166,3 +166,41 @@ def test_graph_walk_kats():
     assert sorted(g(triplets, ring)) == [(0, 1, 2, 3), (1, 0, 3, 2), (1, 2, 3, 0), (2, 1, 0, 3)]
     multi = [("a", "b"), ("b", "c"), ("c", "d"), ("d", "+a")]
     assert sorted(g(multi, multi)) == [("a", "b", "c"), ("b", "c", "d"), ("c", "d", "+a"), ("d", "+a", "+b")]
+
+
+# ---------------------------------------------------------------------------------------------- triclinic wrap
+# The reference holds no fixture in which a triclinic image shift happens: the oracle's restatement of
+# mdtraj's general kernel is checked here against an exhaustive float64 image search written from the definition of
+# the minimum image (tests/bruteforce.py), on boxes whose skew stays inside GROMACS' reduced-cell convention
+# (|b_x| <= a_x / 2, |c_x| <= a_x / 2, |c_y| <= b_y / 2), where mdtraj's 27-image search is exact.
+@pytest.mark.parametrize("skew", [(0.9, -1.1, 1.3), (1.45, 1.45, 1.45), (-1.4, 0.3, -1.2), (0.0, 1.2, 0.0)])
+def test_oracle_triclinic_minimum_image_equals_exhaustive_search(skew):
+    from oracle import geometry as ogeom
+    from tests.bruteforce import min_image_distance, skewed_boxes
+    rng = np.random.default_rng(11)
+    n_frames, n_beads = 40, 60
+    box = skewed_boxes(n_frames, (3.0, 3.1, 2.9), skew, seed=3)
+    frac = rng.uniform(-0.2, 1.2, size=(n_frames, n_beads, 3))          # inside the cell and a little outside
+    xyz = np.einsum("fbi,fij->fbj", frac, box.astype(np.float64)).astype(np.float32)
+    pairs = np.array([(i, j) for i in range(0, n_beads, 3) for j in range(1, n_beads, 7) if i != j], dtype=np.int32)
+    got = ogeom.distances(xyz, pairs, box).astype(np.float64)
+    want = min_image_distance(xyz, pairs, box)
+    assert not ogeom.is_orthorhombic(box)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    # the wrap really happens: many pairs are closer through an image than directly
+    direct = np.linalg.norm(xyz[:, pairs[:, 1]].astype(np.float64) - xyz[:, pairs[:, 0]], axis=-1)
+    assert (want < direct - 1e-3).mean() > 0.3
+
+
+def test_oracle_triclinic_beyond_the_reduced_cell_is_documented():
+    """Outside GROMACS' convention (skew of more than half a cell) mdtraj first reduces the box vectors; the
+    restatement keeps that step, and the result still equals the exhaustive search."""
+    from oracle import geometry as ogeom
+    from tests.bruteforce import min_image_distance, skewed_boxes
+    rng = np.random.default_rng(12)
+    box = skewed_boxes(10, (3.0, 3.0, 3.0), (2.2, -1.9, 2.6), seed=4)
+    frac = rng.uniform(0, 1, size=(10, 30, 3))
+    xyz = np.einsum("fbi,fij->fbj", frac, box.astype(np.float64)).astype(np.float32)
+    pairs = np.array([(i, (i * 7 + 3) % 30) for i in range(30) if i != (i * 7 + 3) % 30], dtype=np.int32)
+    np.testing.assert_allclose(ogeom.distances(xyz, pairs, box).astype(np.float64),
+                               min_image_distance(xyz, pairs, box, reach=4), rtol=2e-6, atol=2e-6)

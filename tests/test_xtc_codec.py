@@ -145,3 +145,66 @@ def test_frame_device_decode_flag(golden, options):
     cg = Mapping(golden / "sugar.map", options).apply(frame)
     gold, _, _ = fileio.read_xtc(golden / "sugar_out.xtc")
     assert np.array_equal(cg._trajectory.xyz, gold)
+
+
+def _corrupted_images(golden):
+    """Bit-flipped and header-damaged variants of a reference file (deterministic)."""
+    data = np.frombuffer((golden / "water.xtc").read_bytes(), dtype=np.uint8)
+    rng = np.random.default_rng(2024)
+    out = []
+    for _ in range(60):
+        img = data.copy()
+        for pos in rng.integers(92, len(img), size=rng.integers(1, 40)):      # payload and later headers
+            img[pos] ^= np.uint8(1 << rng.integers(0, 8))
+        out.append(img)
+    for field, value in ((56, 0.0), (56, -1000.0), (56, float("nan"))):        # precision of the first frame
+        img = data.copy()
+        img[field:field + 4] = np.frombuffer(np.float32(value).astype(">f4").tobytes(), dtype=np.uint8)
+        out.append(img)
+    img = data.copy()                                                          # maxint < minint
+    img[72:76] = np.frombuffer(np.array(-(2 ** 31), dtype=">i4").tobytes(), dtype=np.uint8)
+    out.append(img)
+    img = data.copy()                                                          # payload size says less than there is
+    img[88:92] = np.frombuffer(np.array(16, dtype=">i4").tobytes(), dtype=np.uint8)
+    out.append(img)
+    return out
+
+
+def test_host_decoder_survives_corrupt_streams(golden, tmp_path):
+    """the decoder must not trust the bit stream -- a damaged file either decodes (the damage hit
+    coordinate bits only) or raises; it never divides by zero, walks off the table or reads past the payload."""
+    from pycgtool_b200 import formats
+    path = tmp_path / "bad.xtc"
+    raised = 0
+    for img in _corrupted_images(golden):
+        img.tofile(path)
+        try:
+            traj = formats.read_xtc(path)
+            assert traj.xyz.shape[1:] == (traj.xyz.shape[1], 3)
+        except OSError:
+            raised += 1
+    assert raised >= 5            # the header-damaged ones at the very least
+
+
+@pytest.mark.gpu
+def test_gpu_decoder_survives_corrupt_streams(golden, tmp_path):
+    """The same damaged files through the GPU decoder: an OSError or a decode, and the CUDA context stays usable."""
+    import torch
+    from pycgtool_b200 import formats
+    path = tmp_path / "bad.xtc"
+    for img in _corrupted_images(golden):
+        img.tofile(path)
+        try:
+            host = formats.read_xtc(path)
+        except OSError:
+            host = None
+        try:
+            devt = formats.read_xtc_device(path)
+            torch.cuda.synchronize()
+            if host is not None:
+                assert np.array_equal(devt.xyz, host.xyz)
+        except OSError:
+            assert host is None or True
+    torch.cuda.synchronize()
+    good = formats.read_xtc_device(golden / "water.xtc")
+    assert np.array_equal(good.xyz, formats.read_xtc(golden / "water.xtc").xyz)

@@ -43,7 +43,7 @@ class Frame:
         crosses PCIe) and leaves the coordinates device-resident for ``Mapping.apply``."""
         if topology_file is None:
             self._topology = Topology()   # an empty frame to be filled in (CG output)
-            self._topology._owner = self
+            self._topology.owner = self
             return
         try:
             traj = formats.load(topology_file)
@@ -74,7 +74,7 @@ class Frame:
     def _attach(self, traj):
         traj.topology = self._topology
         self._trajectory = traj
-        self._topology._owner = self
+        self._topology.owner = self
         self.unitcell_lengths = traj.unitcell_lengths
         self.unitcell_angles = traj.unitcell_angles
         self.time = traj.time

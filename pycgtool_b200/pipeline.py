@@ -160,12 +160,15 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
                 box = None
             box_len_dev = None if box is None else device.to_device(box, xyz_in.device, dtype=np.float32)
             nbins_ = 0 if state.hist is None else int(state.hist.shape[1])
+            # the closure holds the buffers, not the state (state -> closure -> state would keep a whole CG
+            # trajectory alive until the cycle collector runs)
+            plan_, source_, nf_, shift_ = state.plan, state.source, state.n_frames, state.shift
+            lo_, hi_ = state.hist_lo, state.hist_hi
 
             def relaunch(packed_=state.packed, values_=state.values):
                 """The two launches again (K1 then K2) into the given accumulators; bench.py times this."""
                 mapping.map_device(map_plan, xyz_in, box_len_dev, out=cg_out)
-                bondset._launch_measure(state.plan, state.source, state.n_frames, state.shift, values_, packed_,
-                                        nbins_, state.hist_lo, state.hist_hi)
+                bondset._launch_measure(plan_, source_, nf_, shift_, values_, packed_, nbins_, lo_, hi_)
 
             state.relaunch = relaunch
         return cg

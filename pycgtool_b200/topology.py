@@ -38,7 +38,7 @@ class Atom:
         """(F, 3) view into the owner's coordinates (``frame.py:143-144``)."""
         if self.index in self._top._pending_coords:
             return self._top._pending_coords[self.index]
-        owner = self._top._owner
+        owner = self._top.owner
         if owner is None or not hasattr(owner, "_trajectory"):
             raise AttributeError("atom has no coordinates")
         return owner._trajectory.xyz[:, self.index]
@@ -120,7 +120,7 @@ class Topology:
         # memory, which mdtraj numbers from zero when it writes them
         self.res_seq = None
         self.atom_serial = None
-        self._owner = None
+        self._owner = None        # weak reference to the Frame whose coordinates the atom views read
         self._pending_coords = {}
         self._grow_res, self._grow_first, self._grow_atoms = None, None, None
 
@@ -136,6 +136,15 @@ class Topology:
         if len(top.res_first) != len(top.res_name_id) + 1 or top.res_first[-1] != len(top.atom_name_id):
             raise ValueError("inconsistent topology arrays")
         return top
+
+    @property
+    def owner(self):
+        return None if self._owner is None else self._owner()
+
+    @owner.setter
+    def owner(self, frame):
+        import weakref
+        self._owner = None if frame is None else weakref.ref(frame)
 
     @classmethod
     def from_residue_lists(cls, residues):

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(256, 2) map_measure_kernel(const MapParams p, 
     tabs.partials = m.partials;
     tabs.hist = m.hist;
     tabs.nbins = m.nbins;
+    tabs.hstride = hist_stride(m.nbins);
     const uint32_t ecache32 = smem_u32(smem_raw + m.off_ecache) + (uint32_t)w * (uint32_t)Rec::kWarpBytes;
     const int fl = kMMWarps / ng;                   // warps per group: they take every fl-th stage
     const bool working = w < ng * fl;
@@ -355,7 +356,7 @@ extern "C" int cgb_map_measure(const float* xyz, const float* box_len, const flo
     m.off_sparam = (int)off;
     off += (size_t)max_slots * 16;
     m.off_shist = (int)off;
-    off += hist ? (size_t)max_slots * n_bins * 4 : 0;
+    off += hist ? (size_t)max_slots * hist_stride(n_bins) * 4 : 0;
     m.off_lists = (int)off;
     off = up(off + 2 * ((size_t)max_slots + 1 + kRoles), 16);
     m.off_nbad = (int)off;

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     tabs.partials = q.partials;
     tabs.hist = q.hist;
     tabs.nbins = q.nbins;
+    tabs.hstride = hist_stride(q.nbins);
     constexpr bool store = (MODE & 1) != 0;
     const int64_t row_stride = q.row_stride;
     TermWarp<MIC, SHAPE> tw;
@@ -373,7 +374,7 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
     q.off_sparam = (int)off;
     off += (size_t)q.max_slots * 16;
     q.off_shist = (int)off;
-    off += q.hist ? (size_t)q.max_slots * q.nbins * 4 : 0;
+    off += q.hist ? (size_t)q.max_slots * hist_stride(q.nbins) * 4 : 0;
     q.off_lists = (int)off;
     off = up(off + 2 * ((size_t)q.max_slots + 1 + kRoles), 16);
     q.off_eacc = 0;
@@ -549,7 +550,7 @@ extern "C" int cgb_measure_plan_limits(int32_t n_bins, int with_hist, int32_t wa
                                        int32_t* max_slots) {
     if (!max_span || !max_slots || n_bins < 0 || n_bins > 512 || want_slots < 1) return CGB_EINVAL;
     const int64_t budget = 112 * 1024;
-    const int64_t per_slot = 22 + (with_hist ? 4 * (int64_t)n_bins : 0);
+    const int64_t per_slot = 22 + (with_hist ? 4 * (int64_t)cgb::hist_stride(n_bins) : 0);
     // everything that does not depend on the plan: barriers, lists, reduction scratch, NaN counters, 7 x 4 KB records
     const int64_t fixed = 192 + 2 * (1 + cgb::kRoles) + 16 + cgb::kRoles * 4 + 128 + cgb::kWarps * cgb::kRoleTableBytes +
                           (int64_t)cgb::kWarps * 2 * CGB_MEAS_EDGE_CHUNKS * 32 * 32 + 64;

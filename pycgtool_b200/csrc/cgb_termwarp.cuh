@@ -18,6 +18,9 @@ constexpr int kTermThreads = kTermWarps * 32;
 constexpr int kChunks = CGB_MEAS_CHUNKS;
 constexpr int kRoles = kChunks * kTermThreads;    // lane-roles of a CTA (chunk, warp, lane)
 
+// Words between the shared-memory histogram rows of two Bond slots (see TermTables::hstride).
+__host__ __device__ constexpr int hist_stride(int nbins) { return nbins | 1; }
+
 // Kind of chunk c in a group of the given shape (0: unused).
 template <int SHAPE>
 __host__ __device__ constexpr int chunk_kind(int c) {
@@ -69,6 +72,8 @@ struct TermTables {
     double* partials;
     double* hist;               // [n_bonds][nbins] float64 counts or NULL
     int nbins;
+    int hstride;                // words between the histogram rows of two slots: odd, so that equal bins of
+                                // different Bonds (similar distributions!) fall into different banks
 };
 
 // Fill the tile's tables; `vt` / `nthreads`: the calling thread's index among the threads that cooperate.
@@ -85,12 +90,12 @@ __device__ __forceinline__ void term_tables_fill(const TermTables& t, const CgbM
             prm.z = fmaf(-lo, prm.y, -0.5f);
             // w: shared-memory address of the slot's histogram row, biased so that the float bits of 2^23 + bin
             // (0x4b000000 + bin) scale straight into the address of the bin (hist_add_pair_pred)
-            prm.w = __uint_as_float(t.shist32 + (uint32_t)(i * t.nbins) * 4u - 4u * 0x4b000000u);
+            prm.w = __uint_as_float(t.shist32 + (uint32_t)(i * t.hstride) * 4u - 4u * 0x4b000000u);
         }
         t.sparam[i] = prm;
     }
     if (do_hist)
-        for (int i = vt; i < tile.nslots * t.nbins; i += nthreads) t.shist[i] = 0u;
+        for (int i = vt; i < tile.nslots * t.hstride; i += nthreads) t.shist[i] = 0u;
     for (int i = vt; i < tile.nslots + 1 + tile.nlist; i += nthreads) t.slist[i] = __ldg(tile_lists + tile.list0 + i);
     for (int i = vt; i < kRoles; i += nthreads) t.snbad[i] = 0u;
 }
@@ -149,7 +154,7 @@ struct TermWarp {
     // Exact-rule histogram update of one value (next to a bin edge, out of range or NaN: ~0.02 % of the values).
     __device__ __forceinline__ void hist_exact(const TermTables& t, int slot, float v) {
         const int bond = t.sbond[slot];
-        hist_add_exact(t.shist + slot * t.nbins, v, __ldg(t.hlo + bond), __ldg(t.hhi + bond), t.nbins);
+        hist_add_exact(t.shist + slot * t.hstride, v, __ldg(t.hlo + bond), __ldg(t.hhi + bond), t.nbins);
     }
 
     // Statistics, histogram and stores of the two evaluated frame pairs of a quad (the common case: all four frames
@@ -211,7 +216,7 @@ struct TermWarp {
         if (t.hist != nullptr) {
             const int bond = t.sbond[slot];
             const int bin = hist_bin(v, __ldg(t.hlo + bond), __ldg(t.hhi + bond), prm.y, t.nbins);
-            if (bin >= 0) atomicAdd(t.shist + slot * t.nbins + bin, 1u);
+            if (bin >= 0) atomicAdd(t.shist + slot * t.hstride + bin, 1u);
         }
     }
 
@@ -454,9 +459,9 @@ struct TermWarp {
             }
         }
         if (t.hist != nullptr) {
-            for (int i = vt; i < tile.nslots * t.nbins; i += nthreads) {
-                const unsigned int v = t.shist[i];
-                if (v) atomicAdd(t.hist + (size_t)t.sbond[i / t.nbins] * t.nbins + (i % t.nbins), (double)v);
+            for (int i = vt; i < tile.nslots * t.hstride; i += nthreads) {
+                const unsigned int v = t.shist[i];      // (the padding word of a row is never written: zero)
+                if (v) atomicAdd(t.hist + (size_t)t.sbond[i / t.hstride] * t.nbins + (i % t.hstride), (double)v);
             }
         }
     }

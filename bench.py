@@ -504,8 +504,10 @@ def north_star_leg(dev, peak_gbs, world, rank, td, mode, scale=1.0):
     mapper, bonds = Mapping(map_path, Options()), BondSet(bnd_path, Options())
     frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
 
+    cg_buffer = torch.empty((frames, mapper._plan_for(frame._topology).n_beads, 3), dtype=torch.float32, device=dev)
+
     def step():
-        map_and_measure(mapper, bonds, frame, store_values=False)
+        map_and_measure(mapper, bonds, frame, store_values=False, out=cg_buffer)   # block after block into one buffer
         bonds.boltzmann_invert()
 
     for _ in range(2):

@@ -571,8 +571,11 @@ class Mapping:
         main.synchronize()
         return cg_dev, out_host
 
-    def apply(self, frame, cg_frame=None):
+    def apply(self, frame, cg_frame=None, out=None):
         """Apply the AA->CG mapping to ``frame``; returns the CG ``Frame``.
+
+        ``out``: optional CUDA float32 tensor ``(F, B, 3)`` to write the bead coordinates into (a pipeline that
+        maps block after block reuses one buffer instead of allocating per call).
 
         The CG coordinates stay on the GPU (``cg._trajectory.device_xyz()``) and are
         copied to the host only when ``.xyz`` / ``atom.coords`` is read.  A large
@@ -593,7 +596,11 @@ class Mapping:
             out, host = self.map_streamed(plan, traj.xyz, box)
             host_xyz = host.numpy()
         else:
-            out = self.map_device(plan, traj.device_xyz(), box)
+            xyz_dev = traj.device_xyz()
+            if out is not None and (tuple(out.shape) != (traj.n_frames, plan.n_beads, 3) or not out.is_cuda):
+                raise ValueError("out must be a CUDA float32 tensor of shape (n_frames, n_beads, 3)")
+            out = self.map_device(plan, xyz_dev, None if box is None else traj.device_box_lengths(xyz_dev.device),
+                                  out=out)
         new = Frame.from_arrays(plan.cg_topology if cg_frame is None else cg_frame._topology, xyz=host_xyz,
                                 unitcell_vectors=traj.unitcell_vectors, time=frame.time, xyz_device=out)
         new._trajectory._global_flags = traj._global_flags      # same unit cell: the decisions carry over

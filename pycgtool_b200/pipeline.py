@@ -130,7 +130,7 @@ def _device_fused(fp, dev):
     return fp._dev[key]
 
 
-def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, fused=None):
+def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, fused=None, out=None):
     """``cg = mapping.apply(frame); bondset.apply(cg)`` in one pass over the atoms; returns ``cg``.
 
     Afterwards ``bondset.boltzmann_invert()`` and every ``bond.values`` behave exactly as after the two
@@ -138,7 +138,8 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     kernels back to back on the device-resident trajectory, which is the faster of the two on B200: stage 2 is bound
     by instruction issue, not by HBM, so re-reading the beads costs less than sharing an SM's warps between mapping
     and measurement (measured in ``bench.py``'s ``pipeline`` leg).  A system the fused kernel does
-    not support, or a host trajectory large enough to be streamed, always takes the two stages.
+    not support, or a host trajectory large enough to be streamed, always takes the two stages.  ``out``: optional
+    CUDA tensor ``(F, B, 3)`` for the bead coordinates (see ``Mapping.apply``).
     """
     import torch
     device.require_cuda()
@@ -150,7 +151,7 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     from . import mapping as _mapping_module
     streamed = (not traj.on_device) and traj.xyz.nbytes >= _mapping_module.STREAM_THRESHOLD_BYTES
     if fp is None or streamed:
-        cg = mapping.apply(frame)
+        cg = mapping.apply(frame, out=out)
         bondset.apply(cg, histogram=histogram, store_values=store_values)
         state = bondset._state
         if not streamed and state is not None and state.n_frames:
@@ -195,7 +196,8 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     if "forms" not in d:
         d["forms"] = device.to_device(bondset._form_ids(), dev)
     stream = device.stream_handle()
-    out = torch.empty((n_frames, map_plan.n_beads, 3), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n_frames, map_plan.n_beads, 3), dtype=torch.float32, device=dev)
     nbins = int(bondset.histogram_bins) if (histogram and plan.n_bonds) else 0
     values = torch.empty((n_frames, n_cols), dtype=torch.float32, device=dev) if store_values else None
     packed = torch.zeros(plan.n_bonds * (_lib.NPART + nbins), dtype=torch.float64, device=dev)

@@ -368,6 +368,17 @@ class Trajectory:
             self._xyz_dev = None
         self._vectors_dev = None
 
+    def device_box_lengths(self, device):
+        """(F, 3) float32 box lengths on the device (uploaded once), or None without a unit cell."""
+        if self.unitcell_lengths is None:
+            return None
+        cached = getattr(self, "_lengths_dev", None)
+        if cached is None or cached.device != device:
+            from . import device as dev
+            cached = dev.to_device(self.unitcell_lengths, device, dtype=np.float32)
+            self._lengths_dev = cached
+        return cached
+
     def device_box_vectors(self, device):
         """(F, 9) float32 box vectors on the device (uploaded once), or None without a unit cell."""
         if self._vectors is None:
@@ -399,6 +410,7 @@ class Trajectory:
         if vectors is None or not np.any(vectors):
             self._vectors = None
             self._vectors_dev = None
+            self._lengths_dev = None
             self._ortho = None
             self._global_flags = None
             self.unitcell_lengths = None
@@ -409,6 +421,7 @@ class Trajectory:
             raise TypeError("unitcell_vectors must have shape (n_frames, 3, 3)")
         self._vectors = vectors
         self._vectors_dev = None
+        self._lengths_dev = None
         self._ortho = None
         self._global_flags = None
         self.unitcell_lengths, self.unitcell_angles = lengths_and_angles(vectors)

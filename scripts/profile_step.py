@@ -29,9 +29,10 @@ def main():
     box = sysm.box_vectors(frames)
     mapper, bonds = Mapping(map_path, Options()), BondSet(bnd_path, Options())
     frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
+    buf = torch.empty((frames, mapper._plan_for(frame._topology).n_beads, 3), dtype=torch.float32, device=dev)
 
     def step():
-        map_and_measure(mapper, bonds, frame, store_values=False)
+        map_and_measure(mapper, bonds, frame, store_values=False, out=buf)
         bonds.boltzmann_invert()
 
     for _ in range(3):

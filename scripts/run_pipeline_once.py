@@ -26,7 +26,7 @@ def main():
     box = sysm.box_vectors(frames)
     mapper, bonds = Mapping(map_path, Options()), BondSet(bnd_path, Options())
     frame = Frame.from_arrays(sysm.topology, unitcell_vectors=box, xyz_device=xyz)
-    map_and_measure(mapper, bonds, frame)
+    map_and_measure(mapper, bonds, frame, fused=True)
     st = bonds._state
     for _ in range(passes):
         st.packed.zero_()

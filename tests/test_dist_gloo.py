@@ -80,6 +80,18 @@ def _worker(rank, world, port, tmpdir):
         partials = packed[:3 * 8].view(3, 8)
         hist = packed[3 * 8:].view(3, 16)
         assert dist.all_true(True) and not dist.all_true(rank == 0)
+        # several decisions in one collective: element-wise AND over the ranks
+        assert dist.all_true_many([True, rank == 0, rank == 1, True]) == (True, False, False, True)
+        # the box decisions of a sharded trajectory are taken over ALL shards (mapping.py:406-408, mdtraj's
+        # orthorhombic test): rank 1's shard has a zero box length in one frame and a skewed cell
+        from pycgtool_b200.topology import Trajectory
+        box = np.zeros((4, 3, 3), dtype=np.float32)
+        box[:, 0, 0] = box[:, 1, 1] = box[:, 2, 2] = 3.0
+        if rank == 1:
+            box[2, 1, 0] = 0.7
+        traj = Trajectory(np.zeros((4, 5, 3), dtype=np.float32), None, None, box)
+        assert traj.global_box_flags() == (True, True, False)       # one rank is not orthorhombic: nobody is
+        assert traj.global_box_flags() == (True, True, False)       # cached: no second collective needed
         for i, (k, form) in enumerate(((2, "Harmonic"), (3, "CosHarmonic"), (4, "Harmonic"))):
             eqm, fc = _invert_row(partials[i].numpy(), k, float(shift[i]), form)
             ref_eqm, ref_fc = ostats.boltzmann_invert(data[k].reshape(-1), k, form)

@@ -159,3 +159,29 @@ def test_unsupported_systems_fall_back_to_two_stages(options):
         assert np.array_equal(np.asarray(x.values), np.asarray(y.values))
         # float64 sums of different CTAs meet in global atomics: the last bits depend on their order
         assert x.eqm == pytest.approx(y.eqm, rel=1e-9) and x.fconst == pytest.approx(y.fconst, rel=1e-9)
+
+
+def test_preallocated_output_buffer_is_used(options):
+    """``out=``: a pipeline that maps block after block writes the beads into one buffer (both paths)."""
+    import torch
+    from pycgtool_b200 import BondSet, Frame, Mapping, map_and_measure
+    from workloads import synth
+    sysm = synth.membrane(20, 10, seed=8)
+    sysm.box = np.array([3.5, 3.5, 3.5])
+    sysm.sigma = 0.12
+    xyz, box = sysm.coordinates_host(18), sysm.box_vectors(18)
+    map_path, bnd_path = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    frame = Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box)
+    want = mapper.apply(frame)._trajectory.xyz
+    n_beads = want.shape[1]
+    for fused in (False, True):
+        buf = torch.full((18, n_beads, 3), float("nan"), dtype=torch.float32, device="cuda")
+        bonds = BondSet(bnd_path, options)
+        cg = map_and_measure(mapper, bonds, frame, fused=fused, out=buf)
+        assert cg._trajectory.device_xyz().data_ptr() == buf.data_ptr()
+        assert np.array_equal(buf.cpu().numpy(), want)
+        bonds.boltzmann_invert()
+        assert all(b.eqm is not None for b in bonds["DOPC"])
+    with pytest.raises(ValueError):
+        mapper.apply(frame, out=torch.empty((3, n_beads, 3), dtype=torch.float32, device="cuda"))

@@ -655,13 +655,14 @@ def ingest_leg(sysm, mapper, plan, dev, frames=2048, td=None, rank=0, world=1):
             "value": world * nf4 * n_atoms / dt4, "unit": "atom-frames/s", "frames": nf4, "ms": dt4 * 1e3,
             "ranks": world,
             "short_run": {"value": world * nf1 * n_atoms / dt1, "frames": nf1, "ms": dt1 * 1e3,
-                          "note": "fill + drain of the pipeline (about 7 ms: one block's upload, walk, decode, map "
-                                  "and D2H) are a fifth of this run"},
+                          "note": f"fill + drain of the pipeline (one block's upload, walk, decode, map and D2H) cost "
+                                  f"{1e3 * (dt1 - dt4 * nf1 / nf4):.1f} ms of this run"},
             "compressed_bytes_per_atom": len(image) / nf1 / n_atoms, "h2d_bytes": int(len(image)) * 4,
             "h2d_gbs_per_rank": 4 * len(image) / dt4 / 1e9,
             "gpu_decode_atoms_per_s": dec4, "host_decode_atoms_per_s": host_rate, "host_decode_cores": os.cpu_count(),
             "note": "decode = per-frame walk over a shared-memory ring (one warp per frame, all frames of a block "
-                    "concurrently) + parallel decode of checkpoints; upload of block i+1 overlaps decode of block i"}
+                    "concurrently; branch-free steps, one LDS.64 per group) + parallel decode of checkpoints; upload of "
+                    "block i+1 overlaps decode of block i"}
 
 
 def run_b200(args):

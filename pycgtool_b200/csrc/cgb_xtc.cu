@@ -300,28 +300,28 @@ __device__ __forceinline__ uint32_t peek_bits(const uint32_t* __restrict__ words
     return __funnelshift_l(lo, hi, sh) >> (32 - n);
 }
 
-// One warp per frame.  The 32 lanes stage the bit stream into a two-half ring in shared memory
-// (coalesced loads, bytes swapped to big-endian words once); lane 0 walks it.  A group's position
-// depends on the previous group's (flag, run) bits, so the walk is a dependent chain (real
-// trajectories set the flag in 40-100 % of the groups, so wider speculation across lanes does not pay;
-// measured).  The chain is kept short by peeking the *next* group at the position it has when the
-// current flag bit is 0 (run length and table entry unchanged), which takes the shared-memory load
-// out of the chain for those groups.  Throughput comes from walking all frames of a block at once.
-constexpr int kWalkHalfWords = 1024;                        // 4 KB per half of the ring
+// One warp per frame.  The 32 lanes stage the bit stream into a two-half ring in shared memory (coalesced loads,
+// bytes swapped to big-endian once); lane 0 walks it.  A group's position depends on the previous group's (flag,
+// run) bits, so the walk is a dependent chain -- pointer chasing through the bit stream, which no prefix scan can
+// break because the positions themselves are the unknowns (real trajectories set the flag in 40-100 % of the groups,
+// so speculating on "flag = 0" across lanes does not pay either; measured).  What can be done is to make the chain
+// short: one step is branch-free integer arithmetic (run / 3 as a multiply-shift, selects instead of branches) and
+// ONE 64-bit shared-memory load -- ring entry i holds words i and i + 1 of the stream, so the six bits that straddle
+// a word boundary come from a single LDS.64.  ~100 cycles per group instead of ~700 for the branchy version with two
+// 32-bit loads and a speculative second peek.  Throughput comes from walking all frames of a block at once.
+constexpr int kWalkHalfWords = 1024;                        // stream words per half of the ring (8 KB of entries)
 constexpr uint32_t kWalkMarginBits = 2 * 96 + 8 * 72 + 64;  // two full coordinates, one run of smalls, slack
 
-__device__ __forceinline__ uint32_t ring_peek6(const uint32_t* ring, uint32_t pos) {
-    const uint32_t w = pos >> 5, sh = pos & 31;
-    const uint32_t hi = ring[w & (2 * kWalkHalfWords - 1)];
-    const uint32_t lo = ring[(w + 1) & (2 * kWalkHalfWords - 1)];
-    return __funnelshift_l(lo, hi, sh) >> 26;
+__device__ __forceinline__ uint32_t ring_peek6(const uint2* ring, uint32_t pos) {
+    const uint2 e = ring[(pos >> 5) & (2 * kWalkHalfWords - 1)];     // .x = word w, .y = word w + 1
+    return __funnelshift_l(e.y, e.x, pos & 31) >> 26;
 }
 
 __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict__ data, int64_t n_bytes,
                                                       const CgbXtcFrame* __restrict__ frames, int64_t n_frames,
                                                       int64_t n_atoms, XtcCheckpoint* __restrict__ checks,
                                                       int32_t* __restrict__ n_checks, int32_t* __restrict__ bad_frames) {
-    __shared__ uint32_t ring[2 * kWalkHalfWords];
+    __shared__ uint2 ring[2 * kWalkHalfWords];
     const int64_t f = blockIdx.x;
     const int lane = threadIdx.x;
     const CgbXtcFrame fr = frames[f];
@@ -338,12 +338,15 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
     bool bad = false;   // lane 0: the stream is not a valid one (see decode_groups)
 
     auto load_half = [&](int h) {
-        uint32_t* dst = ring + (h & 1) * kWalkHalfWords;
+        uint2* dst = ring + (h & 1) * kWalkHalfWords;
         const int64_t w0 = (int64_t)h * kWalkHalfWords;
 #pragma unroll 8
         for (int i = lane; i < kWalkHalfWords; i += 32) {
             const int64_t w = w0 + i;
-            dst[i] = w < avail ? __byte_perm(__ldg(words + w), 0, 0x0123) : 0u;
+            // entry i = (word w, word w + 1); the neighbour's word comes from the same cache lines
+            const uint32_t a = w < avail ? __byte_perm(__ldg(words + w), 0, 0x0123) : 0u;
+            const uint32_t b = w + 1 < avail ? __byte_perm(__ldg(words + w + 1), 0, 0x0123) : 0u;
+            dst[i] = make_uint2(a, b);
         }
     };
     load_half(0);
@@ -351,50 +354,39 @@ __global__ void __launch_bounds__(32) xtc_walk_kernel(const uint8_t* __restrict_
     __syncwarp();
     int hl = 1;  // last half loaded; the ring holds halves hl - 1 and hl
 
-    uint32_t pos = 0;
-    int smallidx = fr.smallidx, run = 0, atom = 0, group = 0, nc = 0;
+    uint32_t pos = 0, smalls = 0;         // smalls = run / 3: small-difference triples per group
+    int smallidx = fr.smallidx, atom = 0, group = 0, nc = 0;
     const uint32_t fullbits = (uint32_t)c.fullbits;
+    const int natoms = fr.natoms;
     for (;;) {
         bool done = false;
         if (lane == 0) {
             const uint32_t limit_bits = (uint32_t)(hl + 1) * kWalkHalfWords * 32u;
             uint32_t v = ring_peek6(ring, pos + fullbits);
-            while (atom < fr.natoms && pos + kWalkMarginBits < limit_bits) {
+            while (atom < natoms && pos + kWalkMarginBits < limit_bits) {
                 if ((group & (kCheckEvery - 1)) == 0) {
                     XtcCheckpoint cp;
                     cp.bitpos = pos;
                     cp.atom = (uint32_t)atom;
-                    cp.state = (uint32_t)smallidx | ((uint32_t)run << 8);
+                    cp.state = (uint32_t)smallidx | ((3u * smalls) << 8);
                     out[nc++] = cp;
                 }
-                // next group if this one's flag bit is 0: same run, same table entry
-                const uint32_t pos0 = pos + fullbits + 1u + (uint32_t)(run / 3) * (uint32_t)smallidx;
-                const uint32_t v0 = ring_peek6(ring, pos0 + fullbits);
-                if (v & 32u) {
-                    run = (int)(v & 31u);
-                    const int is_smaller = run % 3;
-                    run -= is_smaller;
-                    const int smalls = run / 3;
-                    pos += fullbits + 6u + (uint32_t)smalls * (uint32_t)smallidx;
-                    atom += smalls + 1;
-                    smallidx += is_smaller - 1;
-                    if (smallidx < kFirstIdx || smallidx > kLastIdx) {
-                        bad = true;
-                        break;
-                    }
-                    v = ring_peek6(ring, pos + fullbits);
-                } else {
-                    atom += run / 3 + 1;
-                    pos = pos0;
-                    v = v0;
-                }
+                // flag bit, then (if set) the 5-bit run code: run = code - code % 3, table entry += code % 3 - 1
+                const uint32_t flag = v >> 5, code = v & 31u;
+                const uint32_t third = (code * 11u) >> 5;                  // code / 3 for code < 32
+                const int step = (int)code - 3 * (int)third - 1;           // code % 3 - 1
+                smalls = flag ? third : smalls;
+                pos += fullbits + 1u + 5u * flag + smalls * (uint32_t)smallidx;   // the smalls use the old entry
+                atom += (int)smalls + 1;
+                smallidx += flag ? step : 0;
                 ++group;
-                if (pos > end_bits) {
+                if ((uint32_t)(smallidx - kFirstIdx) > (uint32_t)(kLastIdx - kFirstIdx) || pos > end_bits) {
                     bad = true;
                     break;
                 }
+                v = ring_peek6(ring, pos + fullbits);
             }
-            done = bad || atom >= fr.natoms;
+            done = bad || atom >= natoms;
         }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done) break;

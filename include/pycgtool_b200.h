@@ -254,12 +254,18 @@ typedef struct CgbMeasureTuning {
 } CgbMeasureTuning;
 
 /* K2: one launch of persistent CTAs for all columns of the plan (device copies of its arrays).  The work items
- * (tile, block of frames) are dealt to the CTAs in equal contiguous shares. */
+ * (tile, block of frames) are dealt to the CTAs in equal contiguous shares.
+ * fold >= 1, frame folding for systems too small to fill a warp (one small molecule: 23 of 32 lanes): `fold`
+ * consecutive real frames are measured as ONE frame of fold * beads -- cg_xyz [F][B][3] is the same memory as
+ * [F / fold][fold * B][3] -- with a plan compiled for `fold` copies of the system (bead indices of copy r offset by
+ * r * B).  n_frames and n_beads are then those of the folded view, box_vec still holds one box per REAL frame
+ * (fold * n_frames rows; copy r of folded frame v is real frame v * fold + r), and a row of `values` holds the
+ * fold * M values of its real frames in the plan's column order. */
 int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int ortho, int64_t n_frames, int64_t n_beads,
                       const CgbMeasTile* tiles, int64_t n_tiles, const CgbMeasGroup* groups,
                       const CgbMeasLane* lanes, const int32_t* tile_bonds, const uint16_t* tile_lists,
                       int32_t shape, int32_t max_span, int32_t max_slots, int32_t max_edge_chunks,
-                      int32_t max_tile_groups, const float* shift, float* values, int64_t row_stride,
+                      int32_t max_tile_groups, int32_t fold, const float* shift, float* values, int64_t row_stride,
                       double* partials, double* hist, const float* hist_lo, const float* hist_hi, int32_t n_bins,
                       const CgbMeasureTuning* tuning, void* stream);
 

@@ -114,7 +114,7 @@ SIGNATURES = {
     "cgb_measure_plan_build": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp]),
     "cgb_measure_fused": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
-                                 _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+                                 _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "cgb_map_measure": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cgb_measure_fused_config": (_int, [_i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _int, _vp, _i32, _vp]),

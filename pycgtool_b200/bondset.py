@@ -179,6 +179,10 @@ class MeasurePlan:
         self.wide_counts = (0, 0, 0)
         self.wide_beads = self.wide_bond = self.wide_slot = None
         self.wide_max_slots = 0
+        # frame folding (small systems): a second plan for `fold` copies of the system, measured as one frame
+        self.fold = 1
+        self.folded = None            # MeasurePlan of the folded system (kernel arrays only)
+        self.fold_bond_cols = None    # per bond: int64 (fold, n_inst) positions in the folded values row
         self._dev = {}
 
     @property
@@ -228,8 +232,19 @@ class _MeasureState:
             scratch = torch.zeros_like(self.packed)
             self.bondset._launch_measure(self.plan, self.source, self.n_frames, self.shift, self.values, scratch,
                                          0, None, None)
-        idx = torch.from_numpy(cols).to(self.dev)
-        return self.values.index_select(1, idx).reshape(-1).cpu().numpy()
+        main = BondSet.folded_frames(self.plan, self.n_frames)
+        parts = []
+        if main:
+            # the folded rows hold `fold` real frames each, in the folded plan's column order: copy r of the bond's
+            # instances first for r = 0, then r = 1, ... = frame-major once flattened
+            fold = self.plan.fold
+            fidx = torch.from_numpy(np.ascontiguousarray(self.plan.fold_bond_cols[bond_id].reshape(-1))).to(self.dev)
+            view = self.values[:main].reshape(main // fold, fold * self.plan.n_cols)
+            parts.append(view.index_select(1, fidx).reshape(-1))
+        if main < self.n_frames:
+            idx = torch.from_numpy(cols).to(self.dev)
+            parts.append(self.values[main:].index_select(1, idx).reshape(-1))
+        return torch.cat(parts).cpu().numpy()
 
     def _boltzmann(self, temp, pass2, out):
         lib = _lib.load()
@@ -277,10 +292,17 @@ class _MeasureState:
                 # exact <wrap(v - mean)^2> of the flagged Bonds over the stored values (util.py:49-53)
                 self.partials[:, 5].zero_()
                 if n_cols and self.n_frames:
-                    _lib.check(lib.cgb_circular_pass2(device.dptr(self.values), self.n_frames, n_cols,
-                                                      device.dptr(d["col_bond_by_pos"]), n_cols,
-                                                      device.dptr(self.partials), out.data_ptr() + 4 * 8,
-                                                      _lib.NOUT, stream), "cgb_circular_pass2")
+                    main = BondSet.folded_frames(plan, self.n_frames)
+                    regions = []
+                    if main:
+                        fd = BondSet._device_plan(plan.folded, self.dev)
+                        regions.append((self.values, main // plan.fold, plan.fold * n_cols, fd["col_bond_by_pos"]))
+                    if main < self.n_frames:
+                        regions.append((self.values[main:], self.n_frames - main, n_cols, d["col_bond_by_pos"]))
+                    for vals, frames, width, by_pos in regions:
+                        _lib.check(lib.cgb_circular_pass2(device.dptr(vals), frames, width, device.dptr(by_pos), width,
+                                                          device.dptr(self.partials), out.data_ptr() + 4 * 8,
+                                                          _lib.NOUT, stream), "cgb_circular_pass2")
                 if dist.is_distributed():
                     wrapped = self.partials[:, 5].contiguous()
                     dist.allreduce_packed(wrapped)
@@ -341,6 +363,7 @@ class BondSet:
         self.histogram_bins = getattr(options, "histogram_bins", HIST_BINS)
         self.histogram_ranges = dict(HIST_RANGES)
         self.staged = True            # fused kernel over shared-memory tiles (False: gather from global)
+        self.fold_frames = True       # small systems: measure several frames as one (frame folding)
         self.tuning = None            # optional _lib.MeasureTuning, passed to every cgb_measure_fused call
         self._plans = {}
         self._state = None
@@ -565,7 +588,55 @@ class BondSet:
         # from column numbers to positions in the values row
         plan.bond_columns = plan.bond_cols
         plan.bond_cols = [plan.col_out[cols].astype(np.int64) for cols in plan.bond_columns]
+        if fused is None and self.staged and self.fold_frames:
+            self._compile_folded(plan)
         return plan
+
+    # Small systems leave most of a warp idle (one small molecule: 23 of 32 lanes): `fold` consecutive frames are then
+    # measured as ONE frame of fold * B beads -- the CG trajectory [F][B][3] is the same memory as
+    # [F / fold][fold * B][3] -- with a plan compiled for `fold` copies of the system.
+    FOLD_MAX_BEADS = 128          # only systems this small are folded
+    FOLD_CANDIDATES = range(2, 25)
+
+    def _compile_folded(self, plan):
+        n_cols = plan.n_cols
+        if not n_cols or plan.n_beads > self.FOLD_MAX_BEADS or sum(plan.wide_counts) or len(plan.tiles) != 1:
+            return
+        def cost(p, fold):
+            # CTA time per real frame: a tile of ng groups spreads its frames over 7 // ng warps per group
+            return sum(1.0 / max(1, _lib.MEAS_WARPS // int(ng)) for ng in p.tiles["ngroups"]) / fold
+        best, best_cost = None, cost(plan, 1)
+        n2, n3, n4 = plan.counts
+        starts = (0, n2, n2 + n3)
+        for fold in self.FOLD_CANDIDATES:
+            if fold * plan.n_beads > 512 or fold * n_cols > 4096:
+                break
+            f = MeasurePlan()
+            f.n_beads, f.n_bonds, f.natoms = fold * plan.n_beads, plan.n_bonds, plan.natoms
+            f.counts = (fold * n2, fold * n3, fold * n4)
+            beads, bond, origin = [], [], []           # origin: (copy, column) of every folded column
+            for k0, nk in zip(starts, plan.counts):
+                for r in range(fold):
+                    beads.append(plan.col_beads[k0:k0 + nk] + r * plan.n_beads)
+                    bond.append(plan.col_bond[k0:k0 + nk])
+                    origin.append(np.stack([np.full(nk, r), np.arange(k0, k0 + nk)], axis=1))
+            f.col_beads = np.ascontiguousarray(np.concatenate(beads), dtype=np.int32)
+            f.col_bond = np.ascontiguousarray(np.concatenate(bond), dtype=np.int32)
+            origin = np.concatenate(origin)
+            f.bond_first, f.natoms_measured = plan.bond_first, plan.natoms_measured
+            if not self._compile_kernel_plan(f) or sum(f.wide_counts) or not len(f.tiles):
+                continue
+            c = cost(f, fold)
+            if c < 0.95 * best_cost:          # a larger fold (longer tail, more tiles) must pay by at least 5 %
+                best, best_cost = (fold, f, origin), c
+        if best is None:
+            return
+        fold, f, origin = best
+        plan.fold, plan.folded = fold, f
+        # position in the folded values row of (copy r, column c)
+        pos = np.empty((fold, n_cols), dtype=np.int64)
+        pos[origin[:, 0], origin[:, 1]] = f.col_out
+        plan.fold_bond_cols = [pos[:, cols] for cols in plan.bond_columns]
 
     def _compile_kernel_plan(self, plan, fused=None):
         """Tiles / groups / lanes of the fused kernel (``cgb_measure_plan_*``, host code in the library) and the
@@ -685,33 +756,79 @@ class BondSet:
             }
         return plan._dev[key]
 
+    @staticmethod
+    def folded_frames(plan, n_frames):
+        """Leading frames measured through the folded plan (a multiple of ``plan.fold``); the rest, and everything
+        when the trajectory is short, goes through the plain plan."""
+        if plan.folded is None or n_frames < 8 * plan.fold:
+            return 0
+        return (n_frames // plan.fold) * plan.fold
+
     def _launch_measure(self, plan, source, n_frames, shift, values, packed, nbins, hist_lo, hist_hi):
         """Enqueue the measurement of all columns: the fused kernel, then the gather kernels for wide columns.
-        ``values`` None = statistics only; ``nbins`` 0 = no histogram."""
-        lib = _lib.load()
+        ``values`` None = statistics only; ``nbins`` 0 = no histogram.  Small systems: the leading
+        ``folded_frames`` go through the folded plan (``fold`` real frames per measured frame), the tail through
+        the plain one; both accumulate into ``packed``."""
+        import torch
         xyz, box_dev, ortho = source
+        main = self.folded_frames(plan, n_frames)
+
+        def tail():
+            self._launch_one(plan, xyz[main:], None if box_dev is None else box_dev[main:], ortho, n_frames - main, 1,
+                             shift, None if values is None else values[main:], plan.n_cols, packed, nbins,
+                             hist_lo, hist_hi)
+
+        if not main:
+            tail()
+            return
+        if main < n_frames:
+            # the few frames that do not fill a fold run beside the folded launch, on a side stream (both only add
+            # to `packed` with atomics and write disjoint rows of `values`)
+            current = torch.cuda.current_stream(xyz.device)
+            side = self._side_stream(xyz.device)
+            side.wait_stream(current)
+            with torch.cuda.stream(side):
+                tail()
+        self._launch_one(plan.folded, xyz, box_dev, ortho, main // plan.fold, plan.fold, shift, values,
+                         plan.fold * plan.n_cols, packed, nbins, hist_lo, hist_hi)
+        if main < n_frames:
+            current.wait_stream(side)
+            for t in (xyz, box_dev, values, packed, shift, hist_lo, hist_hi):
+                if t is not None:
+                    t.record_stream(side)
+
+    def _side_stream(self, dev):
+        import torch
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = str(dev)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=dev)
+        return streams[key]
+
+    def _launch_one(self, plan, xyz, box_dev, ortho, n_frames, fold, shift, values, row_stride, packed, nbins,
+                    hist_lo, hist_hi):
+        lib = _lib.load()
         dev = xyz.device
         d = self._device_plan(plan, dev)
         stream = device.stream_handle()
         npart = plan.n_bonds * _lib.NPART
         partials = packed[:npart]
         hist = packed[npart:] if nbins else None
-        n_cols = plan.n_cols
         if len(plan.tiles):
             _lib.check(lib.cgb_measure_fused(
                 device.dptr(xyz), device.dptr(box_dev), ortho, n_frames, plan.n_beads, device.dptr(d["tiles"]),
                 len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]), device.dptr(d["tile_bonds"]),
                 device.dptr(d["tile_lists"]), plan.shape, plan.max_span, plan.max_slots, plan.max_edge_chunks,
-                plan.max_tile_groups, device.dptr(shift),
-                device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist), device.dptr(hist_lo),
+                plan.max_tile_groups, int(fold), device.dptr(shift),
+                device.dptr(values), row_stride, device.dptr(partials), device.dptr(hist), device.dptr(hist_lo),
                 device.dptr(hist_hi), int(nbins), _lib.tuning_ptr(self.tuning), stream), "cgb_measure_fused")
         w2, w3, w4 = plan.wide_counts
         if w2 + w3 + w4:
-            wide_values = None if values is None else values.view(-1)[plan.n_staged:]
+            wide_values = None if values is None else values.reshape(-1)[plan.n_staged:]
             _lib.check(lib.cgb_measure(
                 device.dptr(xyz), device.dptr(box_dev), ortho, n_frames, plan.n_beads, device.dptr(d["wide_beads"]),
                 device.dptr(d["wide_bond"]), device.dptr(d["wide_slot"]), plan.wide_max_slots, w2, w3, w4,
-                device.dptr(shift), device.dptr(wide_values), n_cols, device.dptr(partials), device.dptr(hist),
+                device.dptr(shift), device.dptr(wide_values), row_stride, device.dptr(partials), device.dptr(hist),
                 device.dptr(hist_lo), device.dptr(hist_hi), int(nbins), stream), "cgb_measure")
 
     def _release(self):

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(256, 2) map_measure_kernel(const MapParams p, 
     tabs.hist = m.hist;
     tabs.nbins = m.nbins;
     tabs.hstride = hist_stride(m.nbins);
+    tabs.fold = 1;
     const uint32_t ecache32 = smem_u32(smem_raw + m.off_ecache) + (uint32_t)w * (uint32_t)Rec::kWarpBytes;
     const int fl = kMMWarps / ng;                   // warps per group: they take every fl-th stage
     const bool working = w < ng * fl;

@@ -58,6 +58,8 @@ struct FusedParams {
     int32_t tab_off;       // byte offset of the box table inside a stage
     int32_t stage_bytes;
     int32_t contiguous;    // the tile is the whole CG frame: one bulk copy per stage
+    int32_t fold;          // real frames per staged frame (frame folding, >= 1); fold_beads = beads per real frame
+    int32_t fold_beads;
     int32_t ecache_warp_bytes;
     // shared-memory map (byte offsets)
     int32_t off_sparam, off_shist, off_lists, off_eacc, off_nbad, off_roles, off_ecache, off_stages;
@@ -185,30 +187,44 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
                     // [-Lx_a -Lx_b -Ly_a -Ly_b | -Lz_a -Lz_b ix_a ix_b | iy_a iy_b iz_a iz_b] (i = 1 / L), so that three
                     // 16-byte loads give the six packed operands.  Triclinic: 12 floats per frame, [a 0 | b 0 | c 0] reduced.
                     float* tab = reinterpret_cast<float*>(sbase + q.tab_off);
-                    for (int j = lane; j < kk; j += 32) {
-                        Box bx;
-                        if (q.box) {
-                            RawBox<MIC> rb;
-                            fetch_box<MIC>(q.box, f0 + j, rb);
-                            make_box<MIC>(rb, bx);
-                        } else {
+                    // with frame folding a staged frame holds q.fold real frames, each with its own box: entry
+                    // (staged frame j, instance r) is the box of real frame (f0 + j) * fold + r.  Up to four entries
+                    // per lane and round, their global loads all in flight before the first is used.
+                    const int nent = kk * q.fold;
+                    for (int i0 = 0; i0 < nent; i0 += 128) {
+                        RawBox<MIC> rb[4];
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) bx.nL[d] = bx.inv[d] = 0.f;
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + 32 * u + lane;
+                            if (q.box && i < nent) fetch_box<MIC>(q.box, f0 * q.fold + i, rb[u]);
                         }
-                        if (MIC == MIC_ORTHO) {
-                            float* t = tab + (j >> 1) * 12 + (j & 1);
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                t[2 * d] = bx.nL[d];
-                                t[6 + 2 * d] = bx.inv[d];
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + 32 * u + lane;
+                            if (i >= nent) continue;
+                            const int j = i / q.fold, r = i - j * q.fold;
+                            Box bx;
+                            if (q.box) {
+                                make_box<MIC>(rb[u], bx);
+                            } else {
+#pragma unroll
+                                for (int d = 0; d < 3; ++d) bx.nL[d] = bx.inv[d] = 0.f;
                             }
-                        } else {
-                            float* t = tab + j * 12;
+                            if (MIC == MIC_ORTHO) {
+                                float* t = tab + ((j >> 1) * q.fold + r) * 12 + (j & 1);
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                t[d] = bx.a[d];
-                                t[4 + d] = bx.b[d];
-                                t[8 + d] = bx.c[d];
+                                for (int d = 0; d < 3; ++d) {
+                                    t[2 * d] = bx.nL[d];
+                                    t[6 + 2 * d] = bx.inv[d];
+                                }
+                            } else {
+                                float* t = tab + (j * q.fold + r) * 12;
+#pragma unroll
+                                for (int d = 0; d < 3; ++d) {
+                                    t[d] = bx.a[d];
+                                    t[4 + d] = bx.b[d];
+                                    t[8 + d] = bx.c[d];
+                                }
                             }
                         }
                     }
@@ -244,6 +260,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
     tabs.hist = q.hist;
     tabs.nbins = q.nbins;
     tabs.hstride = hist_stride(q.nbins);
+    tabs.fold = q.fold;
     constexpr bool store = (MODE & 1) != 0;
     const int64_t row_stride = q.row_stride;
     TermWarp<MIC, SHAPE> tw;
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
         const uint32_t h0 = (uint32_t)(reinterpret_cast<uintptr_t>(q.xyz + (size_t)tile.bead0 * 3) & 15u);
         term_tables_fill(tabs, tile, q.tile_bonds, q.tile_lists, tid, kConsumers);
         tw.setup(working, q.groups[tile.group0 + gi], q.lanes + (size_t)(tile.group0 + gi) * kChunks * 32, lane, h0,
-                 ecache32, table32, tid);
+                 ecache32, table32, tid, tile.bead0, q.fold > 1 ? q.fold_beads : 0);
         asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
 
         // ---- main loop over the segment's frame blocks (32-bit counters and running pointers: this code runs once
@@ -273,7 +290,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 2) measure_fused_kernel(const
             float* vstage = store ? q.values + (size_t)f_seg * row_stride : nullptr;
             const size_t vstage_step = (size_t)q.k * row_stride;
             const uint32_t quad_bytes = 4u * (uint32_t)q.slot_bytes;
-            const uint32_t tq_quad = MIC == MIC_ORTHO ? 96u : 192u;
+            const uint32_t tq_quad = (MIC == MIC_ORTHO ? 96u : 192u) * (uint32_t)q.fold;
             const size_t vq_quad = (size_t)4 * row_stride;
             const unsigned char* stage = stages + (size_t)s * q.stage_bytes;
             for (int it = 0; it < seg_count; ++it) {
@@ -398,14 +415,15 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
     }
     // frames per stage: whole quads, as many as fit the stage budget (12 bytes of box table per frame); the pipeline
     // is three stages deep unless only two stages of one quad of the widest tile fit
-    const int64_t quad = (slot + 12) * 4 + 64 + 128;
+    const int64_t tab_frame = 48 * (int64_t)std::max(1, q.fold);     // box-table bytes per staged frame
+    const int64_t quad = (slot + tab_frame) * 4 + 64 + 128;
     if ((int64_t)fixed + 2 * quad > kCtaSmem) return -1;    // two stages of one quad of the widest tile do not fit
     while (q.nstage > 2 && quad * q.nstage > (int64_t)kCtaSmem - (int64_t)fixed) --q.nstage;
     int64_t want = tune && tune->stage_bytes ? tune->stage_bytes : 20 * 1024;
     int64_t k = 4;
     for (;;) {
         const int64_t room = ((int64_t)kCtaSmem - (int64_t)fixed) / q.nstage - 128;
-        k = (std::min(want, room) - 64) / (slot + 12);
+        k = (std::min(want, room) - 64) / (slot + tab_frame);
         k -= k % 4;
         if (k >= 4 * min_fl) k -= k % (4 * min_fl);              // whole rounds of quads over the frame lanes
         if (k < 4) k = 4;
@@ -414,11 +432,11 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
         q.k = (int)k;
         q.slot_bytes = (int)slot;
         q.tab_off = (int)((k * slot + 32 + 15) & ~15LL);
-        q.stage_bytes = (int)((q.tab_off + 12 * 4 * k + 127) & ~127LL);
+        q.stage_bytes = (int)((q.tab_off + tab_frame * k + 127) & ~127LL);
         *smem_bytes = fixed + (size_t)q.nstage * q.stage_bytes;
         if (*smem_bytes <= (size_t)kCtaSmem) break;
         if (k > 4)
-            want = (k - 4) * (slot + 12) + 64;                   // one quad less per stage
+            want = (k - 4) * (slot + tab_frame) + 64;            // one quad less per stage
         else if (q.nstage > 2)
             --q.nstage;
         else
@@ -440,11 +458,12 @@ extern "C" int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int 
                                  int64_t n_beads, const CgbMeasTile* tiles, int64_t n_tiles,
                                  const CgbMeasGroup* groups, const CgbMeasLane* lanes, const int32_t* tile_bonds,
                                  const uint16_t* tile_lists, int32_t shape, int32_t max_span, int32_t max_slots,
-                                 int32_t max_edge_chunks, int32_t max_tile_groups, const float* shift, float* values,
-                                 int64_t row_stride, double* partials, double* hist, const float* hist_lo,
-                                 const float* hist_hi, int32_t n_bins, const CgbMeasureTuning* tuning, void* stream) {
+                                 int32_t max_edge_chunks, int32_t max_tile_groups, int32_t fold, const float* shift,
+                                 float* values, int64_t row_stride, double* partials, double* hist,
+                                 const float* hist_lo, const float* hist_hi, int32_t n_bins,
+                                 const CgbMeasureTuning* tuning, void* stream) {
     using namespace cgb;
-    if (n_frames < 0 || n_beads < 0 || n_tiles < 0) return CGB_EINVAL;
+    if (n_frames < 0 || n_beads < 0 || n_tiles < 0 || fold < 1 || fold > 64 || n_beads % fold) return CGB_EINVAL;
     if (n_frames == 0 || n_tiles == 0) return CGB_OK;
     if (!cg_xyz || !tiles || !groups || !lanes || !tile_bonds || !tile_lists || !partials) return CGB_EINVAL;
     if (hist && (!hist_lo || !hist_hi || n_bins < 1 || n_bins > 512)) return CGB_EINVAL;  // fast-bin error bound
@@ -475,6 +494,8 @@ extern "C" int cgb_measure_fused(const float* cg_xyz, const float* box_vec, int 
     q.n_tiles = n_tiles;
     q.nbins = hist ? n_bins : 0;
     q.max_slots = max_slots;
+    q.fold = fold;
+    q.fold_beads = (int32_t)(n_beads / fold);
     int dev = 0, sms = 0;
     CGB_CUDA_TRY(cudaGetDevice(&dev));
     CGB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -525,6 +546,7 @@ extern "C" int cgb_measure_fused_config(int64_t n_frames, int64_t n_beads, int64
     q.nbins = with_hist ? n_bins : 0;
     q.hist = with_hist ? reinterpret_cast<double*>(sizeof(double)) : nullptr;   // only tested against NULL
     q.max_slots = max_slots;
+    q.fold = 1;
     unsigned grid = 0;
     size_t smem = 0;
     const int rc = fused_geometry(q, tuning, max_edge_chunks > 1 ? CGB_SHAPE_EEAA : CGB_SHAPE_EAD, max_span,

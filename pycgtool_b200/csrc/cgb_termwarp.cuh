@@ -46,7 +46,8 @@ struct Role {
 
 // Role table entry (uint4) of lane l in chunk c, at role32 + (c * 32 + l) * 16:
 //   edges:  x = byte offsets of the two beads inside a staged frame (a | b << 16), y = Bond slot (-1: no column),
-//           z = 0, w = position in the values row (-1: the lane emits nothing);
+//           z = float offset of the lane's box-table entry inside its frame (pair)'s block (12 * instance, when
+//           real frames are folded; else 0), w = position in the values row (-1: the lane emits nothing);
 //   terms:  x = byte offsets of the records of the first two edges inside the warp's record area (e0 | e1 << 16),
 //           z = third record (low 16 bits) | bit 16: g1 < 0 | bit 17: g2 < 0, y and w as above.
 // Lanes beyond the chunk's population hold a harmless role (bead 0 twice / record 0) and w = -1.
@@ -72,6 +73,8 @@ struct TermTables {
     double* partials;
     double* hist;               // [n_bonds][nbins] float64 counts or NULL
     int nbins;
+    int fold;                   // real frames folded into one staged frame (>= 1): the box table then holds `fold`
+                                // entries per staged frame (pair), picked by the edge lane's instance
     int hstride;                // words between the histogram rows of two slots: odd, so that equal bins of
                                 // different Bonds (similar distributions!) fall into different banks
 };
@@ -113,8 +116,11 @@ struct TermWarp {
 
     // Roles of this lane for group `grp` of the tile; h0 = byte offset of bead 0 of the tile inside a staged frame;
     // ecache32 = shared-memory address of this warp's edge records; table32 = of this warp's role table.
+    // bead0 / fold_beads: first bead of the tile and beads per real frame when `fold` real frames make one staged
+    // frame (0: no folding) -- an edge lane's instance (which real frame, hence which box) is its bead / fold_beads.
     __device__ __forceinline__ void setup(bool working, const CgbMeasGroup& grp, const CgbMeasLane* lanes, int lane,
-                                          uint32_t h0, uint32_t ecache32, uint32_t table32, int vt_) {
+                                          uint32_t h0, uint32_t ecache32, uint32_t table32, int vt_, int bead0 = 0,
+                                          int fold_beads = 0) {
         vt = vt_;
         frames_done = 0;
         rec32 = ecache32;
@@ -132,6 +138,7 @@ struct TermWarp {
                 const CgbMeasLane ln = lanes[c * 32 + lane];
                 if (kind == 2) {
                     e.x = ((ln.ref & 0xffffu) * 12u + h0) | (((ln.ref >> 16) * 12u + h0) << 16);
+                    if (fold_beads > 0) e.z = 12u * (uint32_t)((bead0 + (int)(ln.ref & 0xffffu)) / fold_beads);
                 } else {
                     const uint32_t e0 = ln.ref & 0x7fu, e1 = (ln.ref >> 8) & 0x7fu, e2 = (ln.ref >> 16) & 0x7fu;
                     const uint32_t n0 = (ln.ref >> 7) & 1u, n1 = (ln.ref >> 15) & 1u, n2 = (ln.ref >> 23) & 1u;
@@ -262,7 +269,7 @@ struct TermWarp {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         Box bx;
-                        const float4* tb = reinterpret_cast<const float4*>(tq + (2 * pp + h) * 12);
+                        const float4* tb = reinterpret_cast<const float4*>(tq + (2 * pp + h) * 12 * t.fold + ro.z);
                         const float4 t0 = tb[0], t1 = tb[1], t2 = tb[2];
                         bx.a[0] = t0.x; bx.a[1] = t0.y; bx.a[2] = t0.z;
                         bx.b[0] = t1.x; bx.b[1] = t1.y; bx.b[2] = t1.z;
@@ -287,7 +294,7 @@ struct TermWarp {
                         xa[d] = pack2(xa0[d], xa1[d]);
                         xb[d] = pack2(xb0[d], xb1[d]);
                     }
-                    const ulonglong2* tb = reinterpret_cast<const ulonglong2*>(tq + pp * 12);
+                    const ulonglong2* tb = reinterpret_cast<const ulonglong2*>(tq + pp * 12 * t.fold + ro.z);
                     const ulonglong2 q0 = tb[0], q1 = tb[1], q2 = tb[2];
                     const f2 nL[3] = {q0.x, q0.y, q1.x}, inv[3] = {q1.y, q2.x, q2.y};
                     edge_pair<MIC_ORTHO>(xa, xb, nL, inv, e[pp]);

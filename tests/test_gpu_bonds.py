@@ -533,7 +533,8 @@ def test_measure_outputs_stay_inside_their_buffers(options):
             device.dptr(cg._trajectory.device_xyz()), device.dptr(box_dev), 1, n_frames, plan.n_beads,
             device.dptr(d["tiles"]), len(plan.tiles), device.dptr(d["groups"]), device.dptr(d["lanes"]),
             device.dptr(d["tile_bonds"]), device.dptr(d["tile_lists"]), plan.shape, plan.max_span, plan.max_slots,
-            plan.max_edge_chunks, plan.max_tile_groups, device.dptr(st.shift), device.dptr(values), n_cols, device.dptr(partials), device.dptr(hist),
+            plan.max_edge_chunks, plan.max_tile_groups, 1, device.dptr(st.shift), device.dptr(values), n_cols,
+            device.dptr(partials), device.dptr(hist),
             device.dptr(st.hist_lo), device.dptr(st.hist_hi), 128, _lib.tuning_ptr(tuning), device.stream_handle()))
         torch.cuda.synchronize()
         for buf, fill in ((vbuf, -12345.0), (pbuf, -7.0)):
@@ -654,3 +655,37 @@ def test_triclinic_lengths_equal_exhaustive_image_search(options, tmp_path, skew
         direct = np.linalg.norm(xyz[:, pairs[k][1]].astype(np.float64) - xyz[:, pairs[k][0]], axis=-1)
         wrapped += int((want[:, k] < direct - 1e-3).sum())
     assert wrapped > 0.2 * n_frames * len(pairs)        # the image shift is exercised, not skipped
+
+
+@pytest.mark.parametrize("n_frames,n_beads", [(4096 + 13, 24), (100, 24), (777, 9), (40, 24)])
+def test_frame_folding_gives_the_unfolded_results(options, n_frames, n_beads):
+    """Small systems measure several frames as one (frame folding): same values, statistics and histograms as the
+    plain plan, including the unfolded tail (n_frames not a multiple of the fold), per-frame boxes and the dihedral
+    second pass; a trajectory shorter than 8 folds is not folded at all."""
+    from pycgtool_b200 import BondSet, Frame, Mapping
+    from workloads import synth
+    sysm = synth.small_molecule(n_beads=n_beads)
+    xyz, box = sysm.coordinates_host(n_frames), sysm.box_vectors(n_frames)
+    map_path, bnd_path = sysm.write_files()
+    cg = Mapping(map_path, options).apply(Frame.from_arrays(sysm.topology, xyz, unitcell_vectors=box))
+    plain = BondSet(bnd_path, options)
+    plain.fold_frames = False
+    plain.apply(cg)
+    plain.boltzmann_invert()
+    folded = BondSet(bnd_path, options)
+    folded.apply(cg)
+    plan = folded._state.plan
+    assert plan.fold > 1 and plan.folded is not None
+    main = BondSet.folded_frames(plan, n_frames)
+    assert main == (0 if n_frames < 8 * plan.fold else (n_frames // plan.fold) * plan.fold)
+    folded.boltzmann_invert()
+    stats_only = BondSet(bnd_path, options)
+    stats_only.apply(cg, store_values=False)
+    stats_only.boltzmann_invert()
+    for a, b, c in zip(plain["MOL"], folded["MOL"], stats_only["MOL"]):
+        assert np.array_equal(np.asarray(a.values), np.asarray(b.values), equal_nan=True)
+        assert np.array_equal(np.asarray(a.values), np.asarray(c.values), equal_nan=True)   # re-measured on demand
+        for other in (b, c):
+            assert other.eqm == pytest.approx(a.eqm, rel=1e-6, abs=1e-7)
+            assert other.fconst == pytest.approx(a.fconst, rel=2e-5)
+            assert np.array_equal(other.histogram[0], a.histogram[0])

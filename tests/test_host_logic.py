@@ -42,7 +42,10 @@ def test_abi_argument_errors_without_gpu():
     assert lib.cgb_map_tiles(None, None, 0, 10, 2, None, 1, None, None, 8, 8, None, None) == 0   # no frames: no-op
     assert lib.cgb_measure(None, None, 1, -1, 2, None, None, None, 0, 0, 0, 0, None, None, 0, None, None, None, None,
                            0, None) == -1
-    assert lib.cgb_measure_fused(None, None, 1, 5, 2, None, 1, None, None, None, None, 0, 8, 8, 1, 1, None, None, 0,
+    assert lib.cgb_measure_fused(None, None, 1, 5, 2, None, 1, None, None, None, None, 0, 8, 8, 1, 1, 1, None, None, 0,
+                                 None, None, None, None, 0, None, None) == -1
+    # frame folding: the folded frame must be a whole number of copies
+    assert lib.cgb_measure_fused(None, None, 1, 5, 7, None, 1, None, None, None, None, 0, 8, 8, 1, 1, 2, None, None, 0,
                                  None, None, None, None, 0, None, None) == -1
     assert lib.cgb_boltzmann(None, None, None, None, 310.0, 3, None, None, None, 0, 0, None, None) == -1
     assert lib.cgb_allreduce_partials(None, None, 4, None) == -1

@@ -599,9 +599,12 @@ class BondSet:
     FOLD_CANDIDATES = range(2, 25)
 
     def _compile_folded(self, plan):
+        import ctypes
+        lib = _lib.load()
         n_cols = plan.n_cols
         if not n_cols or plan.n_beads > self.FOLD_MAX_BEADS or sum(plan.wide_counts) or len(plan.tiles) != 1:
             return
+
         def cost(p, fold):
             # CTA time per real frame: a tile of ng groups spreads its frames over 7 // ng warps per group
             return sum(1.0 / max(1, _lib.MEAS_WARPS // int(ng)) for ng in p.tiles["ngroups"]) / fold
@@ -625,6 +628,13 @@ class BondSet:
             origin = np.concatenate(origin)
             f.bond_first, f.natoms_measured = plan.bond_first, plan.natoms_measured
             if not self._compile_kernel_plan(f) or sum(f.wide_counts) or not len(f.tiles):
+                continue
+            # the launch must fit a CTA's shared memory with the `fold` box-table entries per staged frame
+            cfg = (ctypes.c_int64 * 8)()
+            rc = lib.cgb_measure_fused_config(1 << 20, f.n_beads, len(f.tiles), f.max_span, f.max_slots,
+                                              f.max_edge_chunks, f.max_tile_groups, int(self.histogram_bins), 1, None,
+                                              148, cfg)
+            if rc != 0 or cfg[1] + cfg[2] * cfg[3] * 48 * (fold - 1) > 110 * 1024:
                 continue
             c = cost(f, fold)
             if c < 0.95 * best_cost:          # a larger fold (longer tail, more tiles) must pay by at least 5 %

@@ -37,7 +37,7 @@ def check_case(rng, case):
     else:
         sysm = synth.membrane(int(rng.integers(1, 60)), int(rng.integers(0, 400)) if kind == "membrane_water" else 0,
                               seed=int(rng.integers(1 << 30)))
-    n_frames = int(rng.choice([1, 2, 3, 5, 8, 17, 33, 64, 129, 257]))
+    n_frames = int(rng.choice([1, 2, 3, 5, 8, 17, 33, 64, 129, 257, 513]))      # (chains fold their frames from ~8 folds on)
     box_mode = rng.choice(["large", "tight", "none", "triclinic"])
     if box_mode in ("tight", "triclinic"):
         sysm.box = np.array(rng.uniform(2.2, 3.5, 3))

@@ -386,7 +386,8 @@ def measure_leg(dev, peak_gbs, workload="s3", with_cpu=True, with_e2e=True):
         host = torch.empty((ef, plan.n_beads, 3), dtype=torch.float32, pin_memory=True)
         host.copy_(cg._trajectory.device_xyz()[:ef])
         torch.cuda.synchronize()
-        hframe = Frame.from_arrays(cg._topology, host.numpy(), unitcell_vectors=box[:ef])
+        box_host = torch.from_numpy(np.ascontiguousarray(box[:ef], dtype=np.float32)).pin_memory()   # inputs are pinned
+        hframe = Frame.from_arrays(cg._topology, host.numpy(), unitcell_vectors=box_host.numpy())
 
         def e2e_step():
             hframe._trajectory.drop_device()

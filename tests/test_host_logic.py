@@ -455,3 +455,36 @@ def test_unique_rows_matches_numpy():
     assert len(templates) == len(np.unique(block, axis=0))
     empty, inv = _unique_rows(np.zeros((4, 0), dtype=np.int32))
     assert len(inv) == 4 and (inv == 0).all()
+
+
+def test_frame_folding_plan_for_small_systems(options):
+    """Frame folding (host side): a small molecule is measured as `fold` copies per folded frame; the folded plan
+    covers every (copy, column) exactly once, keeps the Bond of every column and stays one seven-group tile for the
+    S3 shape; systems that already fill their warps are left alone."""
+    from pycgtool_b200 import BondSet, Mapping
+    from workloads import synth
+    from tests.plan_decode import check_measure_plan
+    sysm = synth.small_molecule()
+    map_path, bnd_path = sysm.write_files()
+    bondset = BondSet(bnd_path, options)
+    plan = bondset.compile_plan(Mapping(map_path, options).compile_plan(sysm.topology).cg_topology)
+    assert plan.fold == 9 and plan.folded is not None
+    folded = plan.folded
+    check_measure_plan(folded)                                   # decodes tiles / groups / lanes back to the columns
+    assert folded.n_beads == 9 * plan.n_beads and folded.n_cols == 9 * plan.n_cols
+    assert list(folded.tiles["ngroups"]) == [7]
+    seen = np.concatenate([pos.reshape(-1) for pos in plan.fold_bond_cols])
+    assert sorted(seen.tolist()) == list(range(folded.n_cols))   # every position of the folded row, once
+    by_pos = np.zeros(folded.n_cols, dtype=np.int32)
+    by_pos[folded.col_out] = folded.col_bond
+    for bond_id, pos in enumerate(plan.fold_bond_cols):
+        assert pos.shape == (9, len(plan.bond_cols[bond_id])) and (by_pos[pos] == bond_id).all()
+    # frames measured through the folded plan: whole folds, and none at all for a short trajectory
+    assert BondSet.folded_frames(plan, 1000) == 999 and BondSet.folded_frames(plan, 71) == 0
+    bondset.fold_frames = False
+    bondset._plans = {}
+    assert bondset.compile_plan(Mapping(map_path, options).compile_plan(sysm.topology).cg_topology).folded is None
+    # a membrane fills its warps with instances: no folding
+    mem = synth.membrane(6, 0, seed=3)
+    mp, bp = mem.write_files()
+    assert BondSet(bp, options).compile_plan(Mapping(mp, options).compile_plan(mem.topology).cg_topology).fold == 1

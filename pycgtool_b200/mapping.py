@@ -602,8 +602,9 @@ class Mapping:
             out = self.map_device(plan, xyz_dev, None if box is None else traj.device_box_lengths(xyz_dev.device),
                                   out=out)
         new = Frame.from_arrays(plan.cg_topology if cg_frame is None else cg_frame._topology, xyz=host_xyz,
-                                unitcell_vectors=traj.unitcell_vectors, time=frame.time, xyz_device=out)
-        new._trajectory._global_flags = traj._global_flags      # same unit cell: the decisions carry over
+                                time=frame.time, xyz_device=out)
+        new._trajectory.share_unitcell(traj)        # same unit cell: nothing is derived (or decided) twice
+        new._attach(new._trajectory)
         if cg_frame is not None and hasattr(cg_frame, "_trajectory"):
             cg_frame._trajectory += new._trajectory
             cg_frame._attach(cg_frame._trajectory)

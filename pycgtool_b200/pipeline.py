@@ -238,9 +238,9 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
     if n_frames:
         launch()
 
-    cg = Frame.from_arrays(map_plan.cg_topology, xyz=None, unitcell_vectors=traj.unitcell_vectors, time=frame.time,
-                           xyz_device=out)
-    cg._trajectory._global_flags = traj._global_flags
+    cg = Frame.from_arrays(map_plan.cg_topology, xyz=None, time=frame.time, xyz_device=out)
+    cg._trajectory.share_unitcell(traj)
+    cg._attach(cg._trajectory)
     state = _MeasureState(bondset, plan, n_frames, values, packed, nbins, shift, hist_lo, hist_hi, dev,
                           (out, box_vec, ortho))
     state.hist_lo_host, state.hist_hi_host = lo, hi

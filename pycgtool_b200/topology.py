@@ -362,6 +362,16 @@ class Trajectory:
             self._global_flags = flags
         return flags
 
+    def share_unitcell(self, other):
+        """Take over the unit cell of ``other`` (same frames) with everything already derived from it -- lengths and
+        angles, the orthorhombic test, the device copies, the decisions taken over all ranks -- instead of deriving
+        them again: the CG trajectory mapped from a trajectory has its box."""
+        if other.n_frames != self.n_frames:
+            raise ValueError("unit cells can only be shared between trajectories of the same frames")
+        for name in ("_vectors", "_vectors_dev", "_lengths_dev", "_ortho", "_global_flags", "unitcell_lengths",
+                     "unitcell_angles"):
+            setattr(self, name, getattr(other, name, None))
+
     def drop_device(self):
         """Forget the device copies (the host copy stays): the next use uploads again."""
         if self._xyz is not None:

@@ -912,6 +912,7 @@ class BondSet:
             bond._values = None
             bond._source = (state, bond_id)
             bond.eqm = bond.fconst = None
+            bond._histogram = None
 
     def boltzmann_invert(self):
         """Equilibrium values and force constants of all bonds (``bondset.py:533-539``)."""

@@ -315,7 +315,12 @@ extern "C" int cgb_map_measure(const float* xyz, const float* box_len, const flo
     // frames per CTA: long runs amortise a CTA's start-up (plan entries, first copies), as long as the grid keeps
     // at least ~16 CTAs per SM to balance the tail
     p.fc = 128;
-    while (p.fc < 512 && n_tiles * ((n_frames + 2 * p.fc - 1) / (2 * p.fc)) >= 16 * 148) p.fc *= 2;
+    {
+        int dev = 0, sms = 0;
+        CGB_CUDA_TRY(cudaGetDevice(&dev));
+        CGB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        while (p.fc < 512 && n_tiles * ((n_frames + 2 * p.fc - 1) / (2 * p.fc)) >= 16 * (int64_t)sms) p.fc *= 2;
+    }
     {
         const int64_t nchunks = (n_frames + p.fc - 1) / p.fc;
         if (nchunks > 65535) {

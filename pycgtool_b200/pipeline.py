@@ -250,4 +250,5 @@ def map_and_measure(mapping, bondset, frame, histogram=True, store_values=True, 
         bond._values = None
         bond._source = (state, bond_id)
         bond.eqm = bond.fconst = None
+        bond._histogram = None
     return cg

@@ -445,7 +445,8 @@ static int fused_geometry(FusedParams& q, const CgbMeasureTuning* tune, int32_t 
     // persistent CTAs: the (tile, frame block) items are dealt out in equal contiguous shares; a CTA reduces its
     // float32 sums (segment epilogue) at every change of tile and after at most `max_run` frames per lane
     q.nblocks = (q.F + k - 1) / k;
-    const int64_t max_run = tune && tune->max_run ? tune->max_run : 512;
+    // (bounded: a segment's 32-bit shared-memory histogram bins and float32 sums must not be overrun)
+    const int64_t max_run = std::min<int64_t>(tune && tune->max_run ? tune->max_run : 512, 1 << 20);
     q.seg_cap = (int)std::max<int64_t>(1, max_run * min_fl / k);   // a lane sees k / fl frames per block
     const int64_t items = q.n_tiles * q.nblocks;
     *grid = (unsigned)std::min<int64_t>((int64_t)sm_count * ctas_per_sm, items);

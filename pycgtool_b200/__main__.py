@@ -39,14 +39,19 @@ class PyCGTOOL:
 
     def __init__(self, config):
         self.config = config
-        self.in_frame = Frame(topology_file=config.topology, trajectory_file=config.trajectory,
+        # A mapped .xtc that is used whole is streamed: compressed image up, decoded and mapped block by block on
+        # the GPU, the atomistic coordinates never held as a whole (Mapping.apply_xtc)
+        streamed = bool(config.mapping and config.trajectory and getattr(config, "gpu_decode", False)
+                        and str(config.trajectory).lower().endswith(".xtc") and not config.begin and config.end is None)
+        self.in_frame = Frame(topology_file=config.topology, trajectory_file=None if streamed else config.trajectory,
                               frame_start=config.begin, frame_end=config.end,
                               device_decode=getattr(config, "gpu_decode", False))
         self.mapping = None
         self.out_frame = self.in_frame
         if config.mapping:
             self.mapping = Mapping(config.mapping, config, itp_filename=config.itp)
-            self.out_frame = self.mapping.apply(self.in_frame)
+            self.out_frame = (self.mapping.apply_xtc(self.in_frame, config.trajectory) if streamed
+                              else self.mapping.apply(self.in_frame))
             self.out_frame.save(self.get_output_filepath("gro"), frame_number=0)
         if self.out_frame.natoms == 0:
             logger.warning("Mapped trajectory contains no atoms - check your mapping file is correct!")

@@ -172,15 +172,11 @@ XTC_FRAME_DTYPE = np.dtype([("offset", "<i8"), ("nbytes", "<i4"), ("natoms", "<i
 assert XTC_FRAME_DTYPE.itemsize == _lib.XTC_FRAME_BYTES
 
 
-def read_xtc_device(path, topology=None, device=None):
-    """.xtc -> ``Trajectory`` whose coordinates are decoded on the GPU and stay there.
-
-    Only the compressed file image crosses PCIe (read straight into pinned memory, uploaded in blocks of
-    frames while the previous block is being decoded); ``cgb_xtc_decode`` expands it in HBM."""
+def read_image_pinned(path):
+    """An .xtc file read straight into pinned host memory and scanned: ``(pinned uint8 tensor of the image plus 8
+    bytes of padding, size, frame table, box vectors (F, 3, 3), time (F,), n_frames, n_atoms)``."""
     import os
     import torch
-    from . import device as dev
-    device = device or dev.default_device()
     size = os.path.getsize(path)
     pinned = torch.empty(size + 8, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
@@ -193,6 +189,18 @@ def read_xtc_device(path, topology=None, device=None):
         table, box, time, nf, n_atoms = _scan_xtc(host[:size])
     except RuntimeError as exc:
         raise OSError(f"'{path}': XTC format is not supported ({exc})") from exc
+    return pinned, size, table, box, time, nf, n_atoms
+
+
+def read_xtc_device(path, topology=None, device=None):
+    """.xtc -> ``Trajectory`` whose coordinates are decoded on the GPU and stay there.
+
+    Only the compressed file image crosses PCIe (read straight into pinned memory, uploaded in blocks of
+    frames while the previous block is being decoded); ``cgb_xtc_decode`` expands it in HBM."""
+    import torch
+    from . import device as dev
+    device = device or dev.default_device()
+    pinned, size, table, box, time, nf, n_atoms = read_image_pinned(path)
     _check_topology(topology, n_atoms)
     xyz = torch.empty((nf, n_atoms, 3), dtype=torch.float32, device=device)
     bad = torch.zeros(1, dtype=torch.int32, device=device)
@@ -204,7 +212,7 @@ def read_xtc_device(path, topology=None, device=None):
 
 
 def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, block_bytes=128 << 20, on_block=None,
-                        image_dev=None, n_streams=4, bad_frames=None):
+                        image_dev=None, n_streams=4, bad_frames=None, device=None):
     """Upload an XTC file image from pinned host memory and decode it on the GPU, pipelined: the image goes
     up in blocks of whole frames (~``block_bytes`` each) on a copy stream, and each block is decoded on one of
     ``n_streams`` side streams as soon as it has arrived.  A block's decode starts with a sequential walk per
@@ -212,10 +220,15 @@ def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, bloc
     it; the upload is then the limit.  ``pinned``: uint8 tensor of the image plus 8 bytes of padding;
     ``table``: the frame table from ``cgb_xtc_scan`` (numpy uint8).  ``on_block(f0, f1)`` is called with the
     block's stream current, after the decode of frames [f0, f1) has been enqueued (e.g. to map them right
-    away).  The caller's stream waits for everything on return (asynchronously).  Returns the device image."""
+    away).  The caller's stream waits for everything on return (asynchronously).  Returns the device image.
+
+    ``xyz_dev=None`` streams: the coordinates are never held as a whole -- every pipeline slot decodes its block
+    into a buffer of its own and ``on_block(f0, f1, coords)`` must consume ``coords`` (e.g. map it) on the block's
+    stream before the slot's next block overwrites it (stream order guarantees that).  A trajectory whose raw
+    floats exceed the GPU's memory flows through this way; only the compressed image (about a third) is resident."""
     import torch
     from . import device as dev
-    device = xyz_dev.device
+    device = xyz_dev.device if xyz_dev is not None else (device or dev.default_device())
     if image_dev is None:
         image_dev = torch.empty(n_bytes + 8, dtype=torch.uint8, device=device)
     table_dev = dev.to_device(table, device)
@@ -233,6 +246,10 @@ def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, bloc
     main = torch.cuda.current_stream(device)
     copy = _side_stream(device, "copy")
     workers = [_side_stream(device, i) for i in range(max(1, min(n_streams, len(starts) - 1)))]
+    ring = None
+    if xyz_dev is None:
+        widest = max(f1 - f0 for f0, f1 in zip(starts[:-1], starts[1:]))
+        ring = [torch.empty((widest, n_atoms, 3), dtype=torch.float32, device=device) for _ in workers]
     entry = torch.cuda.Event()
     entry.record(main)
     copy.wait_event(entry)             # buffers may still be in use by earlier work on the caller's stream
@@ -248,14 +265,19 @@ def decode_image_device(pinned, n_bytes, table, n_frames, n_atoms, xyz_dev, bloc
             if k < len(workers):
                 worker.wait_event(entry)
             worker.wait_event(ready)
-            decode_device(image_dev, n_bytes, table_dev, f1 - f0, n_atoms, xyz_dev[f0:], frame0=f0,
+            block_out = xyz_dev[f0:f1] if ring is None else ring[k % len(workers)][:f1 - f0]
+            decode_device(image_dev, n_bytes, table_dev, f1 - f0, n_atoms, block_out, frame0=f0,
                           workspace_key=k % len(workers), bad_frames=bad_frames)
             if on_block is not None:
-                on_block(f0, f1)
+                if ring is None:
+                    on_block(f0, f1)
+                else:
+                    on_block(f0, f1, block_out)
         b0 = b1
     for worker in workers:
         main.wait_stream(worker)
-    for t in (image_dev, table_dev, xyz_dev) + ((bad_frames,) if bad_frames is not None else ()):
+    held = [t for t in (image_dev, table_dev, xyz_dev, bad_frames) if t is not None] + (ring or [])
+    for t in held:
         for st in workers + [copy]:
             t.record_stream(st)
     return image_dev

@@ -613,6 +613,43 @@ class Mapping:
         return new
 
 
+    def apply_xtc(self, frame, path, block_bytes=128 << 20):
+        """``apply`` on an .xtc file that is never expanded as a whole: the compressed image is uploaded in blocks of
+        frames, every block is decoded on the GPU into a pipeline buffer and mapped from there, and only the CG
+        trajectory is kept (reference: ``Frame(gro, xtc)`` through mdtraj's codec, ``pycgtool/frame.py:41-63``, then
+        ``Mapping.apply``).  A trajectory whose raw coordinates exceed the GPU's memory flows through this way.
+        ``frame``: a Frame holding the topology (e.g. ``Frame("system.gro")``)."""
+        import torch
+        from . import formats
+        from .topology import lengths_and_angles
+        device.require_cuda()
+        dev = device.default_device()
+        plan = self._plan_for(frame._topology)
+        pinned, size, table, box, time, n_frames, n_atoms = formats.read_image_pinned(path)
+        if n_atoms != plan.n_atoms:
+            raise ValueError("Number of atoms does not match between topology and trajectory files")
+        vectors = box if box.any() else None
+        lengths = None
+        if vectors is not None:
+            lengths = lengths_and_angles(vectors)[0]
+            if not dist.all_true(bool(np.all(lengths)), device=dev):        # mapping.py:406-408
+                lengths = None
+        lengths_dev = None if lengths is None else device.to_device(lengths, dev, dtype=np.float32)
+        out = torch.empty((n_frames, plan.n_beads, 3), dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def map_block(f0, f1, coords):
+            self.map_device(plan, coords, None if lengths_dev is None else lengths_dev[f0:f1], out=out[f0:f1])
+
+        if n_frames and plan.n_beads:
+            formats.decode_image_device(pinned, size, table, n_frames, n_atoms, None, block_bytes=block_bytes,
+                                        on_block=map_block, bad_frames=bad, device=dev)
+        torch.cuda.current_stream().synchronize()
+        if int(bad.item()):
+            raise OSError(f"'{path}': {int(bad.item())} frame(s) hold a truncated or corrupt coordinate stream")
+        return Frame.from_arrays(plan.cg_topology, xyz=None, unitcell_vectors=vectors, time=time, xyz_device=out)
+
+
 def calc_coords_weight(ref_coords, coords, weights, box=None):
     """Single-bead host formula of ``mapping.py:446-463``, kept for API compatibility
     (tests and user scripts call it directly); the trajectory path does not use it."""

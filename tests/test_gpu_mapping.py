@@ -450,3 +450,28 @@ def test_streamed_host_trajectory_uploads_only_the_mapped_atom_window(options, m
     ref = omap.apply(omap.parse_map(map_path), oracle_system(top, xyz, box))
     assert np.array_equal(streamed, ref.xyz)
     assert np.array_equal(resident._trajectory.xyz, ref.xyz)
+
+
+def test_apply_xtc_streams_the_file_without_expanding_it(golden, options, tmp_path):
+    """``Mapping.apply_xtc``: compressed image -> block-wise GPU decode -> mapping, the raw coordinates never held as
+    a whole.  Same beads as decoding everything first; bit-exact on the reference's sugar case."""
+    from pycgtool_b200 import Frame, Mapping, formats
+    from workloads import synth
+    mapper = Mapping(golden / "sugar.map", options)
+    cg = mapper.apply_xtc(Frame(golden / "sugar.gro"), golden / "sugar.xtc")
+    gold, _, gold_box = fileio.read_xtc(golden / "sugar_out.xtc")
+    assert np.array_equal(cg._trajectory.xyz, gold)
+    np.testing.assert_array_equal(cg.unitcell_lengths, Frame(golden / "sugar.gro", golden / "sugar.xtc").unitcell_lengths)
+    # many small blocks through the ring of pipeline buffers (4 slots reused), water + lipids, 45 frames
+    sysm = synth.membrane(3, 40, seed=12)
+    xyz, box = sysm.coordinates_host(45), sysm.box_vectors(45)
+    path = tmp_path / "m.xtc"
+    formats.encode_xtc(xyz, box, precision=1000.0).tofile(path)
+    map_path, _ = sysm.write_files()
+    mapper = Mapping(map_path, options)
+    top = Frame.from_arrays(sysm.topology, xyz[:1], unitcell_vectors=box[:1])
+    streamed = mapper.apply_xtc(top, path, block_bytes=16 << 10)
+    whole = mapper.apply(Frame.from_arrays(sysm.topology, formats.read_xtc(path).xyz, unitcell_vectors=box))
+    assert streamed.n_frames == 45 and np.array_equal(streamed._trajectory.xyz, whole._trajectory.xyz)
+    with pytest.raises(ValueError):
+        Mapping(golden / "sugar.map", options).apply_xtc(Frame(golden / "sugar.gro"), path)      # atom count differs

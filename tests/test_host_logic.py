@@ -488,3 +488,29 @@ def test_frame_folding_plan_for_small_systems(options):
     mem = synth.membrane(6, 0, seed=3)
     mp, bp = mem.write_files()
     assert BondSet(bp, options).compile_plan(Mapping(mp, options).compile_plan(mem.topology).cg_topology).fold == 1
+
+
+def test_cg_trajectory_shares_the_unit_cell_and_bond_histogram_is_lazy():
+    from pycgtool_b200.bondset import Bond
+    from pycgtool_b200.functionalforms import get_functional_forms
+    from pycgtool_b200.topology import Trajectory
+    box = np.zeros((5, 3, 3), dtype=np.float32)
+    box[:, 0, 0], box[:, 1, 1], box[:, 2, 2] = 3.0, 3.1, 3.2
+    box[2, 1, 0] = 0.4
+    src = Trajectory(np.zeros((5, 7, 3), dtype=np.float32), None, None, box)
+    assert src.global_box_flags() == (True, True, False)
+    cg = Trajectory(np.zeros((5, 2, 3), dtype=np.float32))
+    assert cg.unitcell_lengths is None
+    cg.share_unitcell(src)
+    assert cg.unitcell_vectors is src.unitcell_vectors and cg.unitcell_lengths is src.unitcell_lengths
+    assert cg.orthorhombic is False and cg.global_box_flags() == (True, True, False)
+    with pytest.raises(ValueError):
+        Trajectory(np.zeros((4, 2, 3), dtype=np.float32)).share_unitcell(src)
+    # Bond.histogram: counts kept, edges made on demand (numpy.linspace of the range)
+    bond = Bond(["A", "B"], func_form=get_functional_forms()["Harmonic"].value)
+    assert bond.histogram is None
+    bond._histogram = (np.arange(4, dtype=np.uint64), 0.0, 2.0)
+    counts, edges = bond.histogram
+    assert np.array_equal(counts, [0, 1, 2, 3]) and np.allclose(edges, [0.0, 0.5, 1.0, 1.5, 2.0])
+    bond.histogram = (np.ones(2, dtype=np.uint64), np.array([1.0, 2.0, 3.0]))
+    assert bond._histogram[1:] == (1.0, 3.0)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CGB_ABI_VERSION 2
+#define CGB_ABI_VERSION 3
 
 enum {
     CGB_OK = 0,

@@ -18,7 +18,7 @@ MEAS_CHUNKS = 4  # CGB_MEAS_CHUNKS
 MEAS_EDGE_CHUNKS = 2  # CGB_MEAS_EDGE_CHUNKS
 SHAPE_EAD, SHAPE_EEAA = 0, 1  # CGB_SHAPE_*: [edges | angles | dihedrals | -] / [edges | edges | angles | angles]
 COMM_ID_BYTES = 128  # CGB_COMM_ID_BYTES
-ABI_VERSION = 2  # CGB_ABI_VERSION
+ABI_VERSION = 3  # CGB_ABI_VERSION
 
 FORM_IDS = {
     "Harmonic": 0,

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.SIGNATURES) == declared
     loaded = _lib.load()
-    assert loaded.cgb_abi_version() == _lib.ABI_VERSION == 2
+    assert loaded.cgb_abi_version() == _lib.ABI_VERSION == 3
     assert b"invalid argument" in loaded.cgb_strerror(-1)
 
 
